@@ -1,0 +1,149 @@
+// C ABI of libfbpinn_b200 (see include/fbpinn_b200.h): plan management, validation and dispatch between the
+// tiled (fbp_fast_*.cu) and generic (fbp_generic.cu) kernel families.
+#include "fbp_common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[1024] = "";
+
+void fbp_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+const char* fbp_last_error(void) { return g_err; }
+
+int fbp_version(void) { return 100; }
+
+int fbp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_per_block_optin) {
+    int dev = 0;
+    FBP_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    FBP_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (smem_per_block_optin) *smem_per_block_optin = (int64_t)prop.sharedMemPerBlockOptin;
+    FBP_REQUIRE(prop.major == 10, "libfbpinn_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    return 0;
+}
+
+int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
+    FBP_REQUIRE(out && d, "fbp_plan_create: null argument");
+    *out = nullptr;
+    FBP_REQUIRE(d->xd >= 1 && d->xd <= FBP_MAX_XD, "fbp_plan_create: xd=%d unsupported (1..%d)", d->xd, FBP_MAX_XD);
+    FBP_REQUIRE(d->ud >= 1 && d->ud <= FBP_MAX_UD, "fbp_plan_create: ud=%d unsupported (1..%d)", d->ud, FBP_MAX_UD);
+    FBP_REQUIRE(d->n_layers >= 1 && d->n_layers <= FBP_MAX_LAYERS, "fbp_plan_create: n_layers=%d unsupported (1..%d)",
+                d->n_layers, FBP_MAX_LAYERS);
+    FBP_REQUIRE(d->layer_sizes[0] == d->xd, "fbp_plan_create: layer_sizes[0]=%d must equal xd=%d", d->layer_sizes[0], d->xd);
+    FBP_REQUIRE(d->layer_sizes[d->n_layers] == d->ud, "fbp_plan_create: last layer size %d must equal ud=%d",
+                d->layer_sizes[d->n_layers], d->ud);
+    FBP_REQUIRE(d->activation == FBP_ACT_TANH, "fbp_plan_create: activation %d not implemented (tanh only)", d->activation);
+    FBP_REQUIRE(d->window == FBP_WINDOW_COSINE, "fbp_plan_create: window %d not implemented (cosine only)", d->window);
+    FBP_REQUIRE(d->n_comp >= 1 && d->n_comp <= FBP_MAX_COMP, "fbp_plan_create: n_comp=%d unsupported (1..%d)", d->n_comp, FBP_MAX_COMP);
+    FBP_REQUIRE(d->comp_k[0] < 0 && d->comp_l[0] < 0, "fbp_plan_create: component 0 must be the value");
+
+    fbp_plan* p = new fbp_plan();
+    memset(p, 0, sizeof(*p));
+    p->desc = *d;
+    PlanDev& pd = p->dev;
+    pd.xd = d->xd; pd.ud = d->ud; pd.nl = d->n_layers; pd.ss = 2 * d->xd + 3;
+    int off = 0, hoff = 0;
+    for (int l = 0; l <= d->n_layers; ++l) {
+        if (d->layer_sizes[l] < 1) { delete p; FBP_REQUIRE(false, "fbp_plan_create: layer size must be >= 1"); }
+        pd.size[l] = d->layer_sizes[l];
+    }
+    for (int l = 0; l < d->n_layers; ++l) {
+        pd.woff[l] = off; off += pd.size[l] * pd.size[l + 1];
+        pd.boff[l] = off; off += pd.size[l + 1];
+        if (l < d->n_layers - 1) { pd.hid_off[l] = hoff; hoff += pd.size[l + 1]; }
+    }
+    pd.P = off;
+    pd.hid_total = hoff;
+    pd.C = d->n_comp;
+    // component tables + closure check
+    for (int c = 0; c < d->n_comp; ++c) {
+        int k = d->comp_k[c], l = d->comp_l[c];
+        pd.ck[c] = k; pd.cl[c] = l; pd.i1[c] = 0; pd.i2[c] = 0;
+        pd.ord[c] = (k < 0) ? 0 : (l < 0 ? 1 : 2);
+        bool ok = (c == 0) ? (k < 0 && l < 0) : (k >= 0 && k < d->xd && l < d->xd);
+        if (c > 0 && k < 0) ok = false;
+        if (!ok) { delete p; FBP_REQUIRE(false, "fbp_plan_create: bad jet component %d (k=%d, l=%d)", c, k, l); }
+    }
+    for (int c = 0; c < d->n_comp; ++c) {
+        for (int c2 = 0; c2 < c; ++c2)
+            if (pd.ck[c2] == pd.ck[c] && pd.cl[c2] == pd.cl[c]) { delete p; FBP_REQUIRE(false, "fbp_plan_create: duplicate jet component %d", c); }
+        if (pd.ord[c] != 2) continue;
+        int f1 = -1, f2 = -1;
+        for (int c2 = 0; c2 < d->n_comp; ++c2) {
+            if (pd.ord[c2] == 1 && pd.ck[c2] == pd.ck[c]) f1 = c2;
+            if (pd.ord[c2] == 1 && pd.ck[c2] == pd.cl[c]) f2 = c2;
+        }
+        if (f1 < 0 || f2 < 0) { delete p; FBP_REQUIRE(false, "fbp_plan_create: jet set not closed: order-2 component %d lacks its order-1 components", c); }
+        pd.i1[c] = f1; pd.i2[c] = f2;
+    }
+    p->fast_id = fbp_fast_lookup(d, &p->fast);
+    p->mode = 0;
+    *out = p;
+    return 0;
+}
+
+int fbp_plan_destroy(fbp_plan* plan) {
+    delete plan;
+    return 0;
+}
+
+int64_t fbp_plan_param_count(const fbp_plan* plan) { return plan ? plan->dev.P : -1; }
+int32_t fbp_plan_is_fast(const fbp_plan* plan) { return plan && plan->fast_id >= 0 ? 1 : 0; }
+int32_t fbp_plan_tile_points(const fbp_plan* plan) { return (plan && plan->use_fast()) ? plan->fast.tile_points : 128; }
+
+int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
+    FBP_REQUIRE(plan, "fbp_plan_set_kernel: null plan");
+    FBP_REQUIRE(mode >= 0 && mode <= 2, "fbp_plan_set_kernel: mode must be 0, 1 or 2");
+    FBP_REQUIRE(mode != 2 || plan->fast_id >= 0, "fbp_plan_set_kernel: no tiled kernel instance for this plan");
+    plan->mode = mode;
+    return 0;
+}
+
+int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan) {
+    if (!plan) return -1;
+    return plan->use_fast() ? 0 : (int64_t)plan->dev.hid_total * plan->dev.C;
+}
+
+static int check_view(const fbp_takes_view* tv, const char* who) {
+    FBP_REQUIRE(tv, "%s: null takes view", who);
+    FBP_REQUIRE(tv->s < (1ll << 31) && tv->n < (1ll << 31), "%s: sizes exceed int32 indexing", who);
+    FBP_REQUIRE(tv->m_active >= 0 && tv->m_active <= tv->m_all, "%s: m_active out of range", who);
+    return 0;
+}
+
+int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
+                const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats, void* stream) {
+    FBP_REQUIRE(plan, "fbp_forward: null plan");
+    if (int rc = check_view(tv, "fbp_forward")) return rc;
+    if (plan->use_fast()) return fbp_fast_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, (cudaStream_t)stream);
+    return fbp_generic_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, d_scratch, scratch_floats, (cudaStream_t)stream);
+}
+
+int64_t fbp_backward_workspace_floats(const fbp_plan* plan, const fbp_takes_view* tv) {
+    if (!plan || !tv) return -1;
+    return plan->use_fast() ? fbp_fast_backward_workspace(plan, tv) : 0;
+}
+
+int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
+                 const float* d_sub_static, const float* d_grow, float* d_grads, int32_t accumulate, float* d_gpart,
+                 float* d_scratch, int64_t scratch_floats, void* stream) {
+    FBP_REQUIRE(plan, "fbp_backward: null plan");
+    if (int rc = check_view(tv, "fbp_backward")) return rc;
+    if (plan->use_fast())
+        return fbp_fast_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_gpart, (cudaStream_t)stream);
+    return fbp_generic_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_scratch,
+                                scratch_floats, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+/*
+ * fbpinn_b200.h — C ABI of libfbpinn_b200.so: the FBPINN per-step subdomain evaluation on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the ONE hot path of benmoseley/FBPINNs (v0.2.0, JAX): the work that
+ * the reference performs inside the jitted `FBPINN_update` (fbpinns/trainers.py:285-296) and in the index
+ * construction it depends on.  The reference has no native/FFI layer of its own; the seam these entry
+ * points replace is
+ *      FBPINN_forward(all_params, x_batch, takes, model_fns, jmaps) -> ujs     fbpinns/trainers.py:197-203
+ * under value_and_grad (:292) plus the optimiser lines (:294-295), and, at active-set changes,
+ *      decomposition.inside_points / inside_models                              fbpinns/decompositions.py:201-215
+ *      get_inputs / _get_update_inputs index algebra                            fbpinns/trainers.py:332-391, 544-571
+ * INTEGRATION.md shows the reference-side binding (jax.ffi custom call + custom_vjp, or ctypes).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes only.  Every pointer named d_* is a DEVICE pointer owned by the
+ *    caller; the library never frees or retains caller memory beyond the call (handles excepted).
+ *  - Every function returns 0 on success, non-zero on failure; fbp_last_error() gives the message of the
+ *    last failure on the calling thread.  Nothing throws across the boundary.  There is no CPU fallback.
+ *  - `stream` is a cudaStream_t passed as void*.  All work is enqueued on it; step-path functions
+ *    (window_sums, forward, reduce_*, backward, adam_step, gather/scatter) never allocate, never
+ *    synchronise and are CUDA-graph capturable.  Index-construction functions (fbp_takes_*) may
+ *    allocate scratch and synchronise the stream; they run only when the active set changes.
+ *  - float32 values, int32 indices (JAX defaults, x64 disabled in the reference).
+ *
+ * Data layout (all row-major, contiguous)
+ *  - packed parameters  d_params [m][P]:  per subdomain, for each linear layer l: W_l (out x in, the
+ *    reference's (out,in) leaf, fbpinns/networks.py:55) then b_l (out).  P = sum_l out_l*(in_l+1).
+ *  - static subdomain record d_sub_static [m][2*xd+3]: xmin[xd], xmax[xd], window flag, unnorm mu, unnorm sd
+ *    (float32 casts of fbpinns/decompositions.py:135-181 `params[0,1,4,5]`).
+ *  - jet components: component 0 is the value; a component of order 1 is d/dx_k; order 2 is d2/dx_k dx_l.
+ *    The component set must be closed (an order-2 component needs both its order-1 components) and comes
+ *    from the `jmaps` trie of the constraint's required_ujs (fbpinns/trainers.py:63-107).
+ *  - per-point jets d_ujets [n][C*ud], index c*ud+o.   per-pair numerator jets d_pair_out [s][C*ud] in
+ *    SUBDOMAIN-SORTED pair order.
+ *  - takes (see fbp_takes_emit): reference-order arrays (m_take, n_take, p_take, np_take: bit-exact with
+ *    fbpinns/trainers.py:336-391) plus the subdomain-sorted view the kernels consume.
+ */
+#ifndef FBPINN_B200_H
+#define FBPINN_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBP_MAX_LAYERS 16   /* linear layers */
+#define FBP_MAX_XD 3
+#define FBP_MAX_UD 4
+#define FBP_MAX_COMP 10     /* 1 + xd + xd*(xd+1)/2 at xd = 3 */
+
+#define FBP_ACT_TANH 0      /* FCN, fbpinns/networks.py:61-68 */
+#define FBP_WINDOW_COSINE 0 /* windows.cosine, fbpinns/windows.py:25-35 */
+
+typedef struct fbp_plan fbp_plan;                    /* opaque */
+typedef struct fbp_takes_builder fbp_takes_builder;  /* opaque */
+
+typedef struct fbp_plan_desc {
+    int32_t xd;                                /* input dimension, 1..FBP_MAX_XD */
+    int32_t ud;                                /* output dimension, 1..FBP_MAX_UD */
+    int32_t n_layers;                          /* number of linear layers = len(layer_sizes)-1 */
+    int32_t layer_sizes[FBP_MAX_LAYERS + 1];   /* FCN layer_sizes, fbpinns/networks.py:43 */
+    int32_t activation;                        /* FBP_ACT_* */
+    int32_t window;                            /* FBP_WINDOW_* */
+    int32_t n_comp;                            /* C, jet components incl. the value */
+    int32_t comp_k[FBP_MAX_COMP];              /* first axis, -1 for the value */
+    int32_t comp_l[FBP_MAX_COMP];              /* second axis, -1 unless order 2 */
+} fbp_plan_desc;
+
+/* Kernel-facing view of one constraint's takes (device pointers, see fbp_takes_emit). */
+typedef struct fbp_takes_view {
+    int64_t n;                   /* points in this constraint's x_batch */
+    int64_t s;                   /* (point, subdomain) pairs */
+    int64_t q;                   /* unique (point, pou) rows = len(np_take) */
+    int64_t s_active;            /* pairs of the m_active leading subdomains = sub_off[m_active] */
+    int32_t m_all;               /* subdomains taking part = len(all_ims) (active first, then fixed) */
+    int32_t m_active;            /* leading subdomains that are trained */
+    int32_t npou;                /* global number of partitions of unity */
+    const int32_t* d_m_take;     /* [s] reference order: subdomain position of each pair (trainers.py:372) */
+    const int32_t* d_np_take;    /* [q] reference order: point of each row (trainers.py:385) */
+    const int32_t* d_sub_ids;    /* [m_all] position -> global subdomain index (all_ims) */
+    const int32_t* d_sub_off;    /* [m_all+1] subdomain-sorted pair ranges */
+    const int32_t* d_spair_point;/* [s] point index of each subdomain-sorted pair */
+    const int32_t* d_spair_row;  /* [s] row (p_take value) of each subdomain-sorted pair */
+    const int32_t* d_spair_sub;  /* [s] subdomain position of each subdomain-sorted pair */
+    const int32_t* d_pos;        /* [s] reference-order pair index -> subdomain-sorted pair index */
+    const int32_t* d_row_off;    /* [q+1] reference-order pair range of each row */
+    const int32_t* d_pt_row_off; /* [n+1] row range of each point */
+    const int32_t* d_items;      /* [n_items][4] work list (sub position, first pair, pair count, split id) */
+    const int32_t* d_sub_item_off;/* [m_all+1] item range of each subdomain position */
+    int32_t n_items;             /* built by the host from d_sub_off (fbp_plan_tile_points) */
+    int32_t n_items_active;      /* leading items that belong to active subdomains */
+} fbp_takes_view;
+
+/* ---- errors / info ---------------------------------------------------------------------------- */
+const char* fbp_last_error(void);
+int fbp_version(void);
+/* Device properties the host uses for grid sizing. Fails if no CUDA device / not sm_100. */
+int fbp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_per_block_optin);
+
+/* ---- plan: network shape + jet spec (replaces the static args model_fns / jmaps of
+ *      FBPINN_forward, fbpinns/trainers.py:197, 285) ------------------------------------------- */
+int fbp_plan_create(fbp_plan** plan, const fbp_plan_desc* desc);
+int fbp_plan_destroy(fbp_plan* plan);
+int64_t fbp_plan_param_count(const fbp_plan* plan);       /* P */
+int32_t fbp_plan_is_fast(const fbp_plan* plan);           /* 1 if a tiled kernel instance covers this plan */
+int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile (work-list granularity) */
+/* Select kernel family: 0 = auto (tiled when available), 1 = force generic, 2 = force tiled (error if none). */
+int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode);
+/* Scratch floats the generic kernels need per pair (0 for tiled plans in auto mode). */
+int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan);
+
+/* ---- parameter packing: reference pytree leaves <-> [m][P] (leaves: "layers" list of (w (m,out,in),
+ *      b (m,out)), fbpinns/networks.py:43-47 vmapped at fbpinns/trainers.py:603-607) ------------ */
+int fbp_pack_params(const fbp_plan* plan, int64_t m, const float* const* d_w, const float* const* d_b,
+                    float* d_params, void* stream);
+int fbp_unpack_params(const fbp_plan* plan, int64_t m, const float* d_params, float* const* d_w,
+                      float* const* d_b, void* stream);
+
+/* ---- index construction (A2-A4): inside_points / inside_models / get_inputs on the device --- */
+/* Phase 1: per-point and per-model inside counts of x against the boxes of `d_models` (NULL = all m).
+ *   d_pt_count [n]  = number of selected models containing point i   (inside_ips = count > 0)
+ *   d_model_count [n_models] = number of points inside each selected model (inside_ims = count > 0)
+ * Comparison is the reference's float32 `x >= xmin & x <= xmax` (fbpinns/decompositions.py:217-227). */
+int fbp_inside_count(const float* d_x, int64_t n, int32_t xd, const float* d_sub_static, int32_t m,
+                     const int32_t* d_models, int32_t n_models, int32_t* d_pt_count, int32_t* d_model_count,
+                     void* stream);
+/* Indices of non-zero entries of d_count[n] in ascending order (jnp.arange(n)[mask]); *n_out = how many.
+ * d_out must hold n entries.  Synchronises the stream. */
+int fbp_nonzero_i32(const int32_t* d_count, int64_t n, int32_t* d_out, int64_t* n_out, void* stream);
+/* Row gather: d_dst[i] = d_src[d_idx[i]] for rows of `row_floats` floats (x_batch = x_batch_global[ips]). */
+int fbp_gather_rows(const float* d_src, const int32_t* d_idx, int64_t n_idx, int32_t row_floats, float* d_dst,
+                    void* stream);
+
+/* Phase 2: begin() counts pairs of x against ALL m boxes and returns s (pairs) and q (rows).
+ *   d_pos_of_model [m]: position of each model in all_ims (active first, then fixed), -1 if discarded;
+ *   d_pou_of_model [m]: integer partition-of-unity id (static "pou" leaf, fbpinns/decompositions.py:179).
+ * emit() writes every array of the takes; sizes: m_take,n_take,p_take,spair_*,pos [s]; np_take [q];
+ * row_off [q+1]; pt_row_off [n+1]; sub_off [m_all+1].  Both synchronise the stream. */
+int fbp_takes_begin(fbp_takes_builder** b, const float* d_x, int64_t n, int32_t xd, const float* d_sub_static,
+                    int32_t m, const int32_t* d_pos_of_model, const int32_t* d_pou_of_model, int32_t m_all,
+                    void* stream, int64_t* s_out, int64_t* q_out);
+int fbp_takes_emit(fbp_takes_builder* b, int32_t* d_m_take, int32_t* d_n_take, int32_t* d_p_take,
+                   int32_t* d_np_take, int32_t* d_row_off, int32_t* d_pt_row_off, int32_t* d_sub_off,
+                   int32_t* d_spair_point, int32_t* d_spair_row, int32_t* d_spair_sub, int32_t* d_pos,
+                   void* stream);
+int fbp_takes_destroy(fbp_takes_builder* b);
+
+/* ---- step path (A5-A7 forward, A9 reverse, A10 Adam) ------------------------------------------ */
+/* Denominator jets D = sum_i w_i per row: d_dsum [q][C].  Static between active-set changes
+ * (window_fn has no trainable input, fbpinns/decompositions.py:196-199). */
+int fbp_window_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_sub_static,
+                    float* d_dsum, void* stream);
+
+/* Per-pair numerator jets N_c = d^c(u_i * w_i): norm -> FCN jets -> unnorm -> window jets -> Leibniz.
+ * (FBPINN_model_inner under the nested jvp, fbpinns/trainers.py:113-118, 213-247).
+ * d_pair_out [s][C*ud] in subdomain-sorted order; d_scratch only for generic plans. */
+int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
+                const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats,
+                void* stream);
+
+/* Segment sums + partition-of-unity quotient + /npou (fbpinns/trainers.py:163-170) applied to jets:
+ * per row N = sum of its pairs in REFERENCE order, jets of N/D by the quotient rule, summed over the
+ * point's rows, divided by npou.  d_ujets [n][C*ud] (points without any pair get 0). */
+int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out,
+                       const float* d_dsum, float* d_ujets, void* stream);
+/* Transpose of the above: cotangent of ujets [n][C*ud] -> cotangent of row numerators d_grow [q][C*ud]. */
+int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_ujets_bar,
+                        const float* d_dsum, float* d_grow, void* stream);
+
+/* Reverse pass through the pairs of the ACTIVE subdomains: d_grads [m_active][P] (overwritten when
+ * accumulate == 0, added to otherwise — several constraints share one gradient buffer).
+ * d_gpart: workspace of fbp_backward_workspace_floats() floats (split-subdomain partial sums). */
+int64_t fbp_backward_workspace_floats(const fbp_plan* plan, const fbp_takes_view* tv);
+int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
+                 const float* d_sub_static, const float* d_grow, float* d_grads, int32_t accumulate,
+                 float* d_gpart, float* d_scratch, int64_t scratch_floats, void* stream);
+
+/* optax.adam + apply_updates (fbpinns/trainers.py:294-295, 430) on rows of [.][P]:
+ * for i < n_rows: row r = d_row_ids ? d_row_ids[i] : i of d_params/d_mu/d_nu; gradient row i of d_grads.
+ * d_count: device int32 step counter shared by the whole tree; incremented once per call when
+ * `increment` != 0 (use increment=0 for the 2nd, 3rd ... buffer updated in the same step). */
+int fbp_adam_step(float* d_params, float* d_mu, float* d_nu, const float* d_grads, const int32_t* d_row_ids,
+                  int64_t n_rows, int64_t row_len, int32_t* d_count, int32_t increment, float lr, float b1,
+                  float b2, float eps, float eps_root, void* stream);
+
+/* FP32 FMA pipe micro-benchmark used as the roofline denominator by bench.py: runs `iters` dependent-free
+ * FFMA per thread on a full grid; returns achieved TFLOP/s through *tflops (synchronises). */
+int fbp_fma_peak(int32_t iters, float* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBPINN_B200_H */

@@ -1,0 +1,197 @@
+"""CPU tests: oracle self-checks and the kernel-maths prototype against the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_takes, ref_model, ref_adam
+from fbpinns_b200 import configs
+from fbpinns_b200.jets import JetSpec
+import common
+import proto_kernel_math as proto
+
+
+def test_pair_ordering_matches_dense_nonzero():
+    """The reference's only self-checking code (fbpinns/decompositions_base.py:87-128): n=10000 points in [0,2]^2,
+    m=1000 boxes, pairs must be the row-major non-zeros of the dense inside mask for any batch size."""
+    rng = np.random.default_rng(0)
+    n, m = 10000, 1000
+    x = rng.uniform(0, 2, (n, 2)).astype(np.float32)
+    cc = rng.uniform(1, 3, (m, 2)).astype(np.float32)
+    decomp = {"m": m, "xd": 2, "subdomain": {"params": [cc - np.float32(0.1), cc + np.float32(0.1)], "pou": np.zeros((m, 1), np.float32)}}
+    dense = ref_takes.inside_mask(decomp, x, np.arange(m))
+    nt, mt = np.nonzero(dense)
+    for batch in [1, 9, 10, 128, n]:
+        parts_n, parts_m = [], []
+        for i0, msk in ref_takes._batched(decomp, x, np.arange(m), batch=batch):
+            a, b = np.nonzero(msk)
+            parts_n.append(a + i0)
+            parts_m.append(b)
+            if batch == 1 and i0 > 300:
+                break
+        if batch == 1:
+            k = len(np.concatenate(parts_n))
+            assert (np.concatenate(parts_n) == nt[:k]).all() and (np.concatenate(parts_m) == mt[:k]).all()
+        else:
+            assert (np.concatenate(parts_n) == nt).all() and (np.concatenate(parts_m) == mt).all()
+    n_take, m_take, ims = ref_takes.inside_points(decomp, x)
+    assert (n_take == nt).all() and (m_take == mt).all()
+    assert (ims == np.nonzero(dense.any(0))[0]).all()
+    ips, _ = ref_takes.inside_models(decomp, x, np.arange(m))
+    assert (ips == np.nonzero(dense.any(1))[0]).all()
+
+
+def test_get_jmaps_examples():
+    # Burgers (fbpinns/problems.py:305-310): nodes (0,), (0,0), (1,) -> a 2nd-order chain in x and a 1st-order in t
+    nodes, leaves, jac_is = ref_model.get_jmaps(((0, ()), (0, (0,)), (0, (1,)), (0, (0, 0))))
+    assert nodes == (((0, 0), (0,), 0), ((1, 0), (0, 0), 1), ((0, 1), (1,), 1))
+    assert leaves == ((2, (0, 0)), (3, (1,)))
+    assert jac_is == ((0, 0, 0), (0, 1, 0), (1, 1, 0), (0, 2, 0))
+    nodes, leaves, jac_is = ref_model.get_jmaps(((0, ()),))
+    assert nodes == () and leaves == ((0, ()),) and jac_is == ((0, 0, 0),)
+    from fbpinns_b200.jets import get_jmaps
+    for req in [((0, ()), (0, (0,)), (0, (0, 0))), ((0, (0, 0)), (0, (1, 1)), (0, (2, 2))), ((0, (0, 1)), (1, (1,)))]:
+        assert get_jmaps(req) == ref_model.get_jmaps(req)
+
+
+def test_oracle_jets_against_closed_form():
+    "single subdomain (flag = 0 -> window 1): u = tanh(w z + b) v + c, derivatives in closed form"
+    decomp = ref_takes.rectangular_init_params([np.array([0.5])], [np.array([1.0])], (0.25, 2.0))
+    dt = ref_model.to_torch(decomp, torch.float64)
+    w0, b0, w1, b1 = 0.7, -0.2, 1.3, 0.4
+    layers = [(torch.tensor([[[w0]]], dtype=torch.float64), torch.tensor([[b0]], dtype=torch.float64)),
+              (torch.tensor([[[w1]]], dtype=torch.float64), torch.tensor([[b1]], dtype=torch.float64))]
+    x = torch.linspace(0.1, 0.9, 7, dtype=torch.float64).reshape(-1, 1)
+    takes = (np.zeros(7, np.int32), np.arange(7, dtype=np.int32), np.arange(7, dtype=np.int32), np.arange(7, dtype=np.int32), 1)
+    jm = ref_model.get_jmaps(((0, ()), (0, (0,)), (0, (0, 0))))
+    u, ux, uxx = [t.numpy() for t in ref_model.fbpinn_forward(dt, layers, x, takes, jm)]
+    z = (x.numpy() - 0.5) / 0.5
+    t = np.tanh(w0 * z + b0)
+    g = 1 - t * t
+    assert np.allclose(u, (w1 * t + b1) * 2.0 + 0.25, atol=1e-14)
+    assert np.allclose(ux, 2.0 * w1 * g * w0 / 0.5, atol=1e-13)
+    assert np.allclose(uxx, 2.0 * w1 * (-2 * t * g) * (w0 / 0.5) ** 2, atol=1e-12)
+
+
+def test_adam_closed_form():
+    "first step of Adam moves every parameter by -lr * sign(g) (up to eps); constant gradients keep doing so"
+    p = [np.array([1.0, -2.0, 3.0], dtype=np.float64)]
+    g = [np.array([0.5, -0.25, 2.0], dtype=np.float64)]
+    st = ref_adam.adam_init(p)
+    p1, st = ref_adam.adam_update(g, st, p, learning_rate=1e-3)
+    assert np.allclose(p1[0], p[0] - 1e-3 * np.sign(g[0]), atol=1e-9)
+    assert st["count"] == 1
+    p2, st = ref_adam.adam_update(g, st, p1, learning_rate=1e-3)
+    assert np.allclose(p2[0], p[0] - 2e-3 * np.sign(g[0]), atol=1e-9)
+    # three steps with varying gradient against a straight transcription of the published formulas
+    rng = np.random.default_rng(0)
+    p = [rng.normal(size=5)]
+    st = ref_adam.adam_init(p)
+    m = v = np.zeros(5)
+    pp = p[0].copy()
+    for t in range(1, 4):
+        gg = rng.normal(size=5)
+        p, st = ref_adam.adam_update([gg], st, p)
+        m = 0.9 * m + 0.1 * gg
+        v = 0.999 * v + 0.001 * gg * gg
+        pp = pp - 1e-3 * (m / (1 - 0.9 ** t)) / (np.sqrt(v / (1 - 0.999 ** t)) + 1e-8)
+        assert np.allclose(p[0], pp, rtol=1e-12)
+
+
+CASES = ["cfg1", "cfg2", "cfg3", "cfg5"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_kernel_math_prototype_matches_oracle(name):
+    """forward jets, row sums + quotient rule and the hand-derived reverse pass (what the CUDA kernels compute) agree
+    with the oracle's nested-jvp + autograd formulation in float64."""
+    small = dict(configs.SMALL[name])
+    if name == "cfg3":
+        small.update(n_sub=(3, 3), n_pts=(20, 20), line_scheduler=False)
+    if name == "cfg5":
+        small.update(n_sub=(3, 3), n_pts=(24, 24), layer_sizes=(2, 8, 8, 1))
+    if name == "cfg1":
+        small.update(n_pts=50)
+    if name == "cfg2":
+        small.update(n_sub=6, n_pts=50)
+    k = common.make_case(configs.CONFIGS[name](**small), seed=1)
+    ui = k.ui
+    decomp = k.decomp_np
+    ps = decomp["subdomain"]["params"]
+    ss_all = np.concatenate([ps[0], ps[1], ps[4], ps[5]], axis=1).astype(np.float64)
+    rng = np.random.default_rng(5)
+    for ic, jet in enumerate(k.jets):
+        takes = ui["takess"][ic]
+        m_take, n_take, p_take, np_take, npou = takes
+        if len(m_take) == 0:
+            continue
+        x = ui["constraints"][ic][0].astype(np.float64)
+        im = ui["all_ims"][m_take]
+        lt = [(w[im].astype(np.float64), b[im].astype(np.float64)) for w, b in k.layers]
+        N, cache = proto.pair_forward(jet, x[n_take], ss_all[im], lt)
+        wj = cache["w"]
+        dsum = np.zeros((len(np_take), jet.C))
+        np.add.at(dsum, p_take, wj)
+        ujets = proto.reduce_forward(jet, N, dsum, takes, x.shape[0])
+        ref = common.oracle_ujs(k, ic, torch.float64, constrained=False)
+        for (iu, path), r in zip(jet.required_ujs, ref):
+            got = ujets[:, jet.column(iu, path)]
+            assert common.rel_err(got, r[:, 0]) < 1e-10, (name, ic, path)
+
+        # reverse pass: L = sum_j <R_j, ujs_j>
+        R = [rng.normal(size=(x.shape[0],)) for _ in jet.required_ujs]
+        ubar = np.zeros((x.shape[0], jet.C * jet.ud))
+        for (iu, path), r in zip(jet.required_ujs, R):
+            ubar[:, jet.column(iu, path)] += r
+        grow = proto.reduce_backward(jet, ubar, dsum, takes)
+        m_active = len(ui["active_ims"])
+        grads = proto.pair_backward(jet, lt, cache, grow[p_take], m_take, m_active)
+
+        dtype = torch.float64
+        decomp_cut = ref_model.cut_decomp(ref_model.to_torch(decomp, dtype), ui["all_ims"])
+        lc = [(torch.tensor(w[ui["all_ims"]], dtype=dtype, requires_grad=True),
+               torch.tensor(b[ui["all_ims"]], dtype=dtype, requires_grad=True)) for w, b in k.layers]
+        ujs = ref_model.fbpinn_forward(decomp_cut, lc, torch.as_tensor(x), takes, k.jmapss[ic])
+        L = sum((torch.as_tensor(r).reshape(-1, 1) * u).sum() for r, u in zip(R, ujs))
+        gs = torch.autograd.grad(L, [t for wb in lc for t in wb])
+        for l, (gW, gb) in enumerate(grads):
+            assert common.rel_err(gW, gs[2 * l].numpy()[:m_active]) < 1e-9, (name, ic, l)
+            assert common.rel_err(gb, gs[2 * l + 1].numpy()[:m_active]) < 1e-9, (name, ic, l)
+
+
+def test_kernel_math_prototype_mixed_derivative():
+    "mixed second derivative u_xy (generic kernel family only) through the same formulas"
+    c = configs.cfg5_poisson(n_sub=(3, 3), n_pts=(16, 16), layer_sizes=(2, 8, 1))
+    k = common.make_case(c, seed=2)
+    jet = JetSpec(((0, (0, 1)), (0, (1, 1)), (0, ())), 2, 1)
+    jm = ref_model.get_jmaps(jet.required_ujs)
+    ui = k.ui
+    takes = ui["takess"][0]
+    m_take, n_take, p_take, np_take, npou = takes
+    ps = k.decomp_np["subdomain"]["params"]
+    ss_all = np.concatenate([ps[0], ps[1], ps[4], ps[5]], axis=1).astype(np.float64)
+    x = ui["constraints"][0][0].astype(np.float64)
+    im = ui["all_ims"][m_take]
+    lt = [(w[im].astype(np.float64), b[im].astype(np.float64)) for w, b in k.layers]
+    N, cache = proto.pair_forward(jet, x[n_take], ss_all[im], lt)
+    dsum = np.zeros((len(np_take), jet.C))
+    np.add.at(dsum, p_take, cache["w"])
+    ujets = proto.reduce_forward(jet, N, dsum, takes, x.shape[0])
+    dtype = torch.float64
+    decomp_cut = ref_model.cut_decomp(ref_model.to_torch(k.decomp_np, dtype), ui["all_ims"])
+    lc = [(torch.tensor(w[ui["all_ims"]], dtype=dtype, requires_grad=True),
+           torch.tensor(b[ui["all_ims"]], dtype=dtype, requires_grad=True)) for w, b in k.layers]
+    ujs = ref_model.fbpinn_forward(decomp_cut, lc, torch.as_tensor(x), takes, jm)
+    for (iu, path), r in zip(jet.required_ujs, ujs):
+        assert common.rel_err(ujets[:, jet.column(iu, path)], r.detach().numpy()[:, 0]) < 1e-10, path
+    rng = np.random.default_rng(0)
+    R = [rng.normal(size=(x.shape[0],)) for _ in jet.required_ujs]
+    ubar = np.zeros((x.shape[0], jet.C))
+    for (iu, path), r in zip(jet.required_ujs, R):
+        ubar[:, jet.column(iu, path)] += r
+    grow = proto.reduce_backward(jet, ubar, dsum, takes)
+    grads = proto.pair_backward(jet, lt, cache, grow[p_take], m_take, k.m)
+    L = sum((torch.as_tensor(r).reshape(-1, 1) * u).sum() for r, u in zip(R, ujs))
+    gs = torch.autograd.grad(L, [t for wb in lc for t in wb])
+    for l, (gW, gb) in enumerate(grads):
+        assert common.rel_err(gW, gs[2 * l].numpy()) < 1e-9
+        assert common.rel_err(gb, gs[2 * l + 1].numpy()) < 1e-9
