@@ -106,9 +106,13 @@ def check(rc, what=""):
 
 
 def ptr(t):
-    """Device pointer of a torch tensor (None -> NULL). The tensor must be contiguous and on CUDA."""
+    """Device pointer of a torch tensor (None -> NULL). The tensor must be contiguous, on CUDA, float32 or int32
+    (the only element types the C ABI knows)."""
     if t is None:
         return None
+    import torch
+    if t.dtype not in (torch.float32, torch.int32):
+        raise FbpError(f"libfbpinn_b200 takes float32 / int32 buffers only, got {t.dtype}")
     if not t.is_cuda:
         raise FbpError("libfbpinn_b200 needs CUDA tensors (no CPU path exists)")
     if not t.is_contiguous():

@@ -1,0 +1,698 @@
+// Tiled ("fast") kernel family: the roofline kernels of the FBPINN subdomain evaluation on sm_100a.
+//
+// One CTA per work item = (subdomain, contiguous range of its pairs).  The subdomain's parameters are staged
+// once in shared memory (hidden matrix both transposed and raw), its points are streamed in tiles of TP with
+// coalesced loads, and every linear layer of the jet propagation is a register-tiled FP32 GEMM
+//      A[j][(c,p)] = sum_k W[j][k] * H[k][(c,p)]        j: output unit, c: jet component, p: point of the tile
+// where H lives in shared memory as [k][c][p] (p contiguous: lanes read consecutive points, conflict free) and
+// W^T as [k][j] (a warp reads ONE float4 -> broadcast).  Each thread owns TM=8 output units x PPT=2 points x C
+// components (16*C accumulators), so one k-step costs 2 LDS.128 + C LDS.64 for 16*C FFMA.  tanh jets are applied
+// to the accumulators in registers and written back IN PLACE (one activation buffer per hidden layer).
+//
+// Reverse pass (same CTA shape): recompute the forward keeping h^l per hidden layer, then per layer
+//   G: Wbar[j][k] += sum_{c,p} abar[j][c][p] h[k][c][p]   lanes own an 8x4 (j,k) register tile, warps split the
+//      points, operands read as float4 along p (row stride padded by 4 floats -> the 4/8 distinct rows of a
+//      request fall in distinct banks), accumulators persist in registers across the tiles of the work item;
+//   D: hbar[k][(c,p)] = sum_j W[j][k] abar[j][(c,p)]      same shape as the forward GEMM with the raw matrix;
+//   tanh-jet transpose in registers, written over h^l.
+// First / last layers (K = xd <= 3, M = ud = 1) are not GEMM shaped: they are fused into the epilogues and their
+// gradients are warp-row reductions into shared-memory accumulators.
+// Results per work item go to gpart[item][P]; a second kernel sums the items of a subdomain in fixed order
+// (deterministic, no float atomics anywhere).
+//
+// Bound: FP32 FMA pipe (CUDA cores).  Algorithmic FLOPs per pair: SURVEY §8d (F_fwd = 2 MAC_0 + 2 C sum MAC_l).
+#pragma once
+#include "fbp_common.cuh"
+
+struct FastArgs {
+    const float* x;
+    const float* params;
+    const float* sub_static;
+    const int32_t* sub_ids;
+    const int32_t* spair_point;
+    const int32_t* spair_row;
+    const int32_t* items;
+    float* pair_out;     // forward output  [s][C]
+    const float* grow;   // reverse input   [q][C]
+    float* gpart;        // reverse output  [n_items_active][P]
+    int xd, P;
+    int axis[FBP_MAX_XD];   // slot -> axis (NA2 slots first)
+    int ext[FBP_MAX_COMP];  // internal component -> external component index
+};
+
+template <int H_, int NHID_, int NA2_, int NA1_>
+struct FastCfg {
+    static constexpr int H = H_, NHID = NHID_, NA2 = NA2_, NA1 = NA1_;
+    static constexpr int NS = NA2 + NA1;
+    static constexpr int C = 1 + 2 * NA2 + NA1;
+    static constexpr int TM = 8, PPT = 2, JG = H / TM;
+    static constexpr int HQ = H < 32 ? H : 32;     // quadrant edge of the weight-gradient tiling
+    static constexpr int JJ = HQ / 4, KK = HQ / 8; // per-lane (j,k) register tile of the G phase
+    static constexpr int QW = H / HQ, NQ = QW * QW;
+
+    // small-parameter block shared by both kernels (floats)
+    static constexpr int SM_W0 = 0;                          // [3][H]  first-layer weights, axis major
+    static constexpr int SM_B0 = SM_W0 + 3 * H;              // [H]
+    static constexpr int SM_W0D = SM_B0 + H;                 // [max(NS,1)][H]  W0[:,axis]*inv_sd
+    static constexpr int SM_WT1 = SM_W0D + (NS > 0 ? NS : 1) * H;   // [H][H] hidden matrix transposed (k major)
+    static constexpr int SM_WR1 = SM_WT1 + (NHID == 2 ? H * H : 0); // [H][H] hidden matrix raw (j major)
+    static constexpr int SM_B1 = SM_WR1 + (NHID == 2 ? H * H : 0);  // [H]
+    static constexpr int SM_WL = SM_B1 + (NHID == 2 ? H : 0);       // [H] output weights
+    static constexpr int SM_BL = SM_WL + H;                         // [4] output bias (+pad)
+    static constexpr int SM_PARAMS = SM_BL + 4;
+
+    // forward tile: largest TP in {128, 64, 32} whose footprint allows 2 CTAs per SM when possible
+    static constexpr int fwd_floats(int tp) {
+        return SM_PARAMS + 3 * tp + (NHID == 2 ? H * C * tp : 0) + JG * C * tp + C * tp;
+    }
+    static constexpr bool fwd_ok(int tp) { return fwd_floats(tp) * 4 <= 110 * 1024 && JG * (tp / PPT) <= 256; }
+    static constexpr int TPF = fwd_ok(128) ? 128 : (fwd_ok(64) ? 64 : 32);
+    static constexpr int NTF = JG * (TPF / PPT);
+    static constexpr int FWD_MINB = fwd_ok(TPF) ? 2 : 1;
+
+    // backward tile
+    static constexpr int SM_GRAD = 3 * H + H + (NS > 0 ? NS : 1) * H + (NHID == 2 ? H : 0) + H + 4;   // T, B0, S, B1, WL, BL
+    static constexpr int bwd_floats(int tp) {
+        return SM_PARAMS + SM_GRAD + 3 * tp + C * tp + NHID * H * (C * tp + 4);
+    }
+    static constexpr bool bwd_ok(int tp) { return bwd_floats(tp) * 4 <= 200 * 1024 && JG * (tp / PPT) <= 256; }
+    static constexpr int TPB = bwd_ok(128) ? 128 : (bwd_ok(64) ? 64 : 32);
+    static constexpr int NTB = JG * (TPB / PPT);
+};
+
+__device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
+
+// window value / first / second derivative per slot for one point
+template <class CF>
+__device__ __forceinline__ void fast_window(const float z[3], const float isd[3], int xd, float flag, const int axis[FBP_MAX_XD],
+                                            float& w, float w1[CF::NS > 0 ? CF::NS : 1], float w2[CF::NA2 > 0 ? CF::NA2 : 1]) {
+    float f[3], f1[3], f2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < xd) fbp_window_dim(z[d], isd[d], f[d], f1[d], f2[d]);
+        else { f[d] = 1.0f; f1[d] = 0.0f; f2[d] = 0.0f; }
+    }
+    const float fall = f[0] * f[1] * f[2];
+    w = flag * fall + (1.0f - flag);
+#pragma unroll
+    for (int s = 0; s < CF::NS; ++s) {
+        const int ax = axis[s];
+        const float others = flag * sel3(ax, f[1] * f[2], f[0] * f[2], f[0] * f[1]);
+        w1[s] = others * sel3(ax, f1[0], f1[1], f1[2]);
+        if (s < CF::NA2) w2[s] = others * sel3(ax, f2[0], f2[1], f2[2]);
+    }
+}
+
+// Stage the subdomain's parameters in shared memory.
+template <class CF, int NT>
+__device__ __forceinline__ void fast_load_params(float* sm, const float* __restrict__ prow, int xd, const float isd[3],
+                                                 const int axis[FBP_MAX_XD], bool want_raw) {
+    constexpr int H = CF::H;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 3 * H; i += NT) sm[CF::SM_W0 + i] = 0.0f;
+    __syncthreads();
+    for (int i = tid; i < H * xd; i += NT) {
+        int j = i / xd, d = i - j * xd;
+        sm[CF::SM_W0 + d * H + j] = prow[i];
+    }
+    for (int i = tid; i < H; i += NT) sm[CF::SM_B0 + i] = prow[H * xd + i];
+    for (int i = tid; i < CF::NS * H; i += NT) {
+        int s = i / H, j = i - s * H;
+        int ax = axis[s];
+        sm[CF::SM_W0D + i] = prow[j * xd + ax] * sel3(ax, isd[0], isd[1], isd[2]);
+    }
+    int off = H * xd + H;
+    if (CF::NHID == 2) {
+        for (int i = tid; i < H * H; i += NT) {
+            int j = i / H, k = i - j * H;
+            float v = prow[off + i];
+            sm[CF::SM_WT1 + k * H + j] = v;
+            if (want_raw) sm[CF::SM_WR1 + i] = v;
+        }
+        off += H * H;
+        for (int i = tid; i < H; i += NT) sm[CF::SM_B1 + i] = prow[off + i];
+        off += H;
+    }
+    for (int i = tid; i < H; i += NT) sm[CF::SM_WL + i] = prow[off + i];
+    if (tid == 0) sm[CF::SM_BL] = prow[off + H];
+}
+
+// tanh jets applied in place to the accumulators of one (unit, point): a -> h
+template <class CF>
+__device__ __forceinline__ void fast_tanh_jets(float (&a)[CF::C]) {
+    const float t = fbp_tanh(a[0]);
+    const float g = 1.0f - t * t;
+    a[0] = t;
+#pragma unroll
+    for (int s = 0; s < CF::NA2; ++s) {
+        const float a1 = a[1 + 2 * s], a2 = a[2 + 2 * s];
+        a[1 + 2 * s] = g * a1;
+        a[2 + 2 * s] = g * (a2 - 2.0f * t * a1 * a1);
+    }
+#pragma unroll
+    for (int s = 0; s < CF::NA1; ++s) a[1 + 2 * CF::NA2 + s] *= g;
+}
+
+// transpose of fast_tanh_jets: h (forward outputs), hb (their cotangents) -> ab (cotangents of the pre-activations)
+template <class CF>
+__device__ __forceinline__ void fast_tanh_jets_bwd(const float (&h)[CF::C], const float (&hb)[CF::C], float (&ab)[CF::C]) {
+    const float t = h[0];
+    const float g = 1.0f - t * t;
+    float ab0 = g * hb[0];
+#pragma unroll
+    for (int s = 0; s < CF::NA2; ++s) {
+        const float h1 = h[1 + 2 * s], h2 = h[2 + 2 * s];
+        const float b1 = hb[1 + 2 * s], b2 = hb[2 + 2 * s];
+        ab[2 + 2 * s] = g * b2;
+        ab[1 + 2 * s] = g * b1 - 4.0f * t * b2 * h1;
+        ab0 -= 2.0f * t * b1 * h1 + 2.0f * b2 * (t * h2 + h1 * h1);
+    }
+#pragma unroll
+    for (int s = 0; s < CF::NA1; ++s) {
+        const int c = 1 + 2 * CF::NA2 + s;
+        ab[c] = g * hb[c];
+        ab0 -= 2.0f * t * hb[c] * h[c];
+    }
+    ab[0] = ab0;
+}
+
+// First layer + tanh jets for TM units x PPT points into acc (registers).
+template <class CF, int TP>
+__device__ __forceinline__ void fast_layer0(const float* sm, const float* zs, int j0, int p0,
+                                            float (&acc)[CF::TM][CF::PPT][CF::C]) {
+    constexpr int H = CF::H;
+    float z[3][CF::PPT];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float2 v = *reinterpret_cast<const float2*>(zs + d * TP + p0);
+        z[d][0] = v.x;
+        z[d][1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < CF::TM; ++j) {
+        const float w0 = sm[CF::SM_W0 + j0 + j], w1 = sm[CF::SM_W0 + H + j0 + j], w2 = sm[CF::SM_W0 + 2 * H + j0 + j];
+        const float b = sm[CF::SM_B0 + j0 + j];
+        float wd[CF::NS > 0 ? CF::NS : 1];
+#pragma unroll
+        for (int s = 0; s < CF::NS; ++s) wd[s] = sm[CF::SM_W0D + s * H + j0 + j];
+#pragma unroll
+        for (int p = 0; p < CF::PPT; ++p) {
+            float a[CF::C];
+            a[0] = fmaf(w2, z[2][p], fmaf(w1, z[1][p], fmaf(w0, z[0][p], b)));
+#pragma unroll
+            for (int s = 0; s < CF::NA2; ++s) { a[1 + 2 * s] = wd[s]; a[2 + 2 * s] = 0.0f; }
+#pragma unroll
+            for (int s = 0; s < CF::NA1; ++s) a[1 + 2 * CF::NA2 + s] = wd[CF::NA2 + s];
+            fast_tanh_jets<CF>(a);
+#pragma unroll
+            for (int c = 0; c < CF::C; ++c) acc[j][p][c] = a[c];
+        }
+    }
+}
+
+// acc[j][p][c] = sum_k Wm[k*H + j0 + j] * act[k*RS + c*TP + p0 + p]   (Wm: k-major matrix in shared memory)
+template <class CF, int TP, int RS>
+__device__ __forceinline__ void fast_gemm(const float* __restrict__ Wm, const float* __restrict__ act, int j0, int p0,
+                                          float (&acc)[CF::TM][CF::PPT][CF::C]) {
+    constexpr int H = CF::H;
+#pragma unroll
+    for (int j = 0; j < CF::TM; ++j)
+#pragma unroll
+        for (int p = 0; p < CF::PPT; ++p)
+#pragma unroll
+            for (int c = 0; c < CF::C; ++c) acc[j][p][c] = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+        const float4 wa = *reinterpret_cast<const float4*>(Wm + k * H + j0);
+        const float4 wb = *reinterpret_cast<const float4*>(Wm + k * H + j0 + 4);
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        float2 av[CF::C];
+#pragma unroll
+        for (int c = 0; c < CF::C; ++c) av[c] = *reinterpret_cast<const float2*>(act + k * RS + c * TP + p0);
+#pragma unroll
+        for (int j = 0; j < CF::TM; ++j)
+#pragma unroll
+            for (int c = 0; c < CF::C; ++c) {
+                acc[j][0][c] = fmaf(w[j], av[c].x, acc[j][0][c]);
+                acc[j][1][c] = fmaf(w[j], av[c].y, acc[j][1][c]);
+            }
+    }
+}
+
+template <class CF, int TP, int RS>
+__device__ __forceinline__ void fast_store_act(float* act, int j0, int p0, const float (&acc)[CF::TM][CF::PPT][CF::C]) {
+#pragma unroll
+    for (int j = 0; j < CF::TM; ++j)
+#pragma unroll
+        for (int c = 0; c < CF::C; ++c)
+            *reinterpret_cast<float2*>(act + (j0 + j) * RS + c * TP + p0) = make_float2(acc[j][0][c], acc[j][1][c]);
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <class CF>
+__global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(FastArgs a) {
+    constexpr int H = CF::H, C = CF::C, TM = CF::TM, PPT = CF::PPT, JG = CF::JG, TP = CF::TPF, NT = CF::NTF;
+    constexpr int RS = C * TP;
+    extern __shared__ __align__(16) float sm[];
+    float* zs = sm + CF::SM_PARAMS;                       // [3][TP]
+    float* act = zs + 3 * TP;                             // [H][RS]      (NHID == 2)
+    float* part = act + (CF::NHID == 2 ? H * RS : 0);     // [JG][C][TP]
+    float* outN = part + JG * C * TP;                     // [TP][C] in external component order
+
+    const int tid = threadIdx.x;
+    const int item = blockIdx.x;
+    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
+    const int im = a.sub_ids[sp];
+    const int xd = a.xd;
+    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < xd) {
+            const float lo = ss[d], hi = ss[xd + d];
+            mu[d] = (hi + lo) * 0.5f;
+            isd[d] = 1.0f / ((hi - lo) * 0.5f);
+        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
+    }
+    const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
+    fast_load_params<CF, NT>(sm, a.params + (int64_t)im * a.P, xd, isd, a.axis, false);
+    __syncthreads();
+
+    const int jg = tid / (TP / PPT), pp = tid % (TP / PPT);
+    const int j0 = jg * TM, p0 = pp * PPT;
+
+    for (int t0 = 0; t0 < count; t0 += TP) {
+        const int cnt = min(TP, count - t0);
+        if (tid < TP) {
+            const int pt = a.spair_point[first + t0 + (tid < cnt ? tid : 0)];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) zs[d * TP + tid] = d < xd ? (a.x[(int64_t)pt * xd + d] - mu[d]) * isd[d] : 0.0f;
+        }
+        __syncthreads();
+
+        float acc[TM][PPT][C];
+        fast_layer0<CF, TP>(sm, zs, j0, p0, acc);
+        if (CF::NHID == 2) {
+            fast_store_act<CF, TP, RS>(act, j0, p0, acc);
+            __syncthreads();
+            fast_gemm<CF, TP, RS>(sm + CF::SM_WT1, act, j0, p0, acc);
+#pragma unroll
+            for (int j = 0; j < TM; ++j) {
+                const float b = sm[CF::SM_B1 + j0 + j];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    acc[j][p][0] += b;
+                    fast_tanh_jets<CF>(acc[j][p]);
+                }
+            }
+        }
+        // output layer (ud = 1): partial dot over this thread's TM units, reduced over the JG groups below
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < TM; ++j) {
+                const float wl = sm[CF::SM_WL + j0 + j];
+                s0 = fmaf(wl, acc[j][0][c], s0);
+                s1 = fmaf(wl, acc[j][1][c], s1);
+            }
+            *reinterpret_cast<float2*>(part + (jg * C + c) * TP + p0) = make_float2(s0, s1);
+        }
+        __syncthreads();
+
+        if (tid < TP) {
+            float u[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float r = (c == 0) ? sm[CF::SM_BL] : 0.0f;
+#pragma unroll
+                for (int g = 0; g < JG; ++g) r += part[(g * C + c) * TP + tid];
+                u[c] = un_sd * r;
+            }
+            u[0] += un_mu;
+            float z[3] = {zs[tid], zs[TP + tid], zs[2 * TP + tid]};
+            float w, w1[CF::NS > 0 ? CF::NS : 1], w2[CF::NA2 > 0 ? CF::NA2 : 1];
+            fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
+            float* o = outN + tid * C;
+            o[a.ext[0]] = u[0] * w;
+#pragma unroll
+            for (int s = 0; s < CF::NA2; ++s) {
+                const float u1 = u[1 + 2 * s], u2 = u[2 + 2 * s];
+                o[a.ext[1 + 2 * s]] = u1 * w + u[0] * w1[s];
+                o[a.ext[2 + 2 * s]] = u2 * w + 2.0f * u1 * w1[s] + u[0] * w2[s];
+            }
+#pragma unroll
+            for (int s = 0; s < CF::NA1; ++s) {
+                const int c = 1 + 2 * CF::NA2 + s;
+                o[a.ext[c]] = u[c] * w + u[0] * w1[CF::NA2 + s];
+            }
+        }
+        __syncthreads();
+        float* dst = a.pair_out + (int64_t)(first + t0) * C;
+        for (int i = tid; i < cnt * C; i += NT) dst[i] = outN[i];
+    }
+}
+
+// =====================================================================================================
+// reverse
+// =====================================================================================================
+template <class CF>
+__global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
+    constexpr int H = CF::H, C = CF::C, TM = CF::TM, PPT = CF::PPT, JG = CF::JG, TP = CF::TPB, NT = CF::NTB;
+    constexpr int NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
+    constexpr int RS = C * TP + 4;
+    constexpr int NW = NT / 32;
+    constexpr int JJ = CF::JJ, KK = CF::KK, HQ = CF::HQ, QW = CF::QW, NQ = CF::NQ;
+    constexpr int PG = NW / NQ;          // point groups of the G phase
+    constexpr int PPG = TP / PG;         // points per group
+    static_assert(NW % NQ == 0 && PG >= 1 && PPG % 4 == 0, "bad G-phase tiling");
+    static_assert(NT >= TP, "point stage needs NT >= TP");
+
+    extern __shared__ __align__(16) float sm[];
+    float* gs = sm + CF::SM_PARAMS;                  // small-layer gradient accumulators
+    float* gT = gs;                                  // [3][H]  sum abar0 * z_d
+    float* gB0 = gT + 3 * H;                         // [H]
+    float* gS = gB0 + H;                             // [NS][H] sum abar_first per slot
+    float* gB1 = gS + (NS > 0 ? NS : 1) * H;         // [H] (NHID == 2)
+    float* gWL = gB1 + (CF::NHID == 2 ? H : 0);      // [H]
+    float* gBL = gWL + H;                            // [4]
+    float* zs = gs + CF::SM_GRAD;                    // [3][TP]
+    float* rb = zs + 3 * TP;                         // [C][TP]   cotangent of the output-layer jets
+    float* act0 = rb + C * TP;                       // [H][RS]
+    float* act1 = act0 + H * RS;                     // [H][RS]   (NHID == 2)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x;
+    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
+    const int im = a.sub_ids[sp];
+    const int xd = a.xd;
+    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < xd) {
+            const float lo = ss[d], hi = ss[xd + d];
+            mu[d] = (hi + lo) * 0.5f;
+            isd[d] = 1.0f / ((hi - lo) * 0.5f);
+        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
+    }
+    const float flag = ss[2 * xd], un_sd = ss[2 * xd + 2];
+    fast_load_params<CF, NT>(sm, a.params + (int64_t)im * a.P, xd, isd, a.axis, true);
+    for (int i = tid; i < CF::SM_GRAD; i += NT) gs[i] = 0.0f;
+    __syncthreads();
+
+    const int jg = tid / (TP / PPT), pp = tid % (TP / PPT);
+    const int j0 = jg * TM, p0 = pp * PPT;
+    float* actL = CF::NHID == 2 ? act1 : act0;       // activations of the last hidden layer
+
+    // G-phase ownership
+    const int qd = warp % NQ, pg = warp / NQ;
+    const int qj = qd / QW, qk = qd % QW;
+    const int jt = lane >> 3, kt = lane & 7;
+    float gacc[JJ][KK];
+    float bacc[JJ];
+#pragma unroll
+    for (int jj = 0; jj < JJ; ++jj) {
+        bacc[jj] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) gacc[jj][kk] = 0.0f;
+    }
+
+    for (int t0 = 0; t0 < count; t0 += TP) {
+        const int cnt = min(TP, count - t0);
+        // ---- S0: points, window jets, cotangent of the output jets ------------------------------------
+        if (tid < TP) {
+            const bool valid = tid < cnt;
+            const int pi = first + t0 + (valid ? tid : 0);
+            const int pt = a.spair_point[pi];
+            float z[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                z[d] = d < xd ? (a.x[(int64_t)pt * xd + d] - mu[d]) * isd[d] : 0.0f;
+                zs[d * TP + tid] = z[d];
+            }
+            float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
+            fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
+            const float* gr = a.grow + (int64_t)a.spair_row[pi] * C;
+            float G[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) G[c] = valid ? gr[a.ext[c]] : 0.0f;
+            float ub0 = G[0] * w;
+#pragma unroll
+            for (int s = 0; s < NA2; ++s) {
+                const float G1 = G[1 + 2 * s], G2 = G[2 + 2 * s];
+                ub0 += G1 * w1[s] + G2 * w2[s];
+                rb[(1 + 2 * s) * TP + tid] = un_sd * (G1 * w + 2.0f * G2 * w1[s]);
+                rb[(2 + 2 * s) * TP + tid] = un_sd * (G2 * w);
+            }
+#pragma unroll
+            for (int s = 0; s < NA1; ++s) {
+                const int c = 1 + 2 * NA2 + s;
+                ub0 += G[c] * w1[NA2 + s];
+                rb[c * TP + tid] = un_sd * (G[c] * w);
+            }
+            rb[tid] = un_sd * ub0;
+        }
+        __syncthreads();
+
+        // ---- forward recompute -------------------------------------------------------------------------
+        float acc[TM][PPT][C];
+        fast_layer0<CF, TP>(sm, zs, j0, p0, acc);
+        fast_store_act<CF, TP, RS>(act0, j0, p0, acc);
+        if (CF::NHID == 2) {
+            __syncthreads();
+            fast_gemm<CF, TP, RS>(sm + CF::SM_WT1, act0, j0, p0, acc);
+#pragma unroll
+            for (int j = 0; j < TM; ++j) {
+                const float b = sm[CF::SM_B1 + j0 + j];
+#pragma unroll
+                for (int p = 0; p < PPT; ++p) {
+                    acc[j][p][0] += b;
+                    fast_tanh_jets<CF>(acc[j][p]);
+                }
+            }
+            fast_store_act<CF, TP, RS>(act1, j0, p0, acc);
+        }
+        __syncthreads();
+
+        // ---- output layer gradients: rows k over warps, points over lanes -------------------------------
+        for (int k = warp; k < H; k += NW) {
+            float s = 0.0f;
+            for (int p = lane; p < TP; p += 32) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) s = fmaf(rb[c * TP + p], actL[k * RS + c * TP + p], s);
+            }
+            s = fbp_warp_sum(s);
+            if (lane == 0) gWL[k] += s;
+        }
+        if (warp == 0) {
+            float s = 0.0f;
+            for (int p = lane; p < TP; p += 32) s += rb[p];
+            s = fbp_warp_sum(s);
+            if (lane == 0) gBL[0] += s;
+        }
+        __syncthreads();
+
+        // ---- tanh transpose of the last hidden layer, in place: actL <- abar ----------------------------
+#pragma unroll
+        for (int j = 0; j < TM; ++j) {
+            const float wl = sm[CF::SM_WL + j0 + j];
+            float2 hv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) hv[c] = *reinterpret_cast<const float2*>(actL + (j0 + j) * RS + c * TP + p0);
+            float2 rv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) rv[c] = *reinterpret_cast<const float2*>(rb + c * TP + p0);
+            float h0[C], h1[C], b0[C], b1[C], o0[C], o1[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { h0[c] = hv[c].x; h1[c] = hv[c].y; b0[c] = wl * rv[c].x; b1[c] = wl * rv[c].y; }
+            fast_tanh_jets_bwd<CF>(h0, b0, o0);
+            fast_tanh_jets_bwd<CF>(h1, b1, o1);
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                *reinterpret_cast<float2*>(actL + (j0 + j) * RS + c * TP + p0) = make_float2(o0[c], o1[c]);
+        }
+        __syncthreads();
+
+        if (CF::NHID == 2) {
+            // ---- G: Wbar1[j][k] += sum_{c,p} abar1[j][c][p] * h0[k][c][p] ; bbar1[j] += sum_p abar1[j][0][p]
+            {
+                const float* ab = act1 + (qj * HQ + jt) * RS;
+                const float* hp = act0 + (qk * HQ + kt) * RS;
+                for (int pq = pg * PPG; pq < (pg + 1) * PPG; pq += 4) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        float4 av[JJ], hv[KK];
+#pragma unroll
+                        for (int jj = 0; jj < JJ; ++jj) av[jj] = *reinterpret_cast<const float4*>(ab + (4 * jj) * RS + c * TP + pq);
+#pragma unroll
+                        for (int kk = 0; kk < KK; ++kk) hv[kk] = *reinterpret_cast<const float4*>(hp + (8 * kk) * RS + c * TP + pq);
+#pragma unroll
+                        for (int jj = 0; jj < JJ; ++jj) {
+#pragma unroll
+                            for (int kk = 0; kk < KK; ++kk) {
+                                float g = gacc[jj][kk];
+                                g = fmaf(av[jj].x, hv[kk].x, g);
+                                g = fmaf(av[jj].y, hv[kk].y, g);
+                                g = fmaf(av[jj].z, hv[kk].z, g);
+                                g = fmaf(av[jj].w, hv[kk].w, g);
+                                gacc[jj][kk] = g;
+                            }
+                            if (c == 0) bacc[jj] += (av[jj].x + av[jj].y) + (av[jj].z + av[jj].w);
+                        }
+                    }
+                }
+            }
+            // ---- D: hbar0[k][(c,p)] = sum_j W1[j][k] abar1[j][(c,p)]  (raw matrix is "j-major" = k contiguous)
+            fast_gemm<CF, TP, RS>(sm + CF::SM_WR1, act1, j0, p0, acc);
+            __syncthreads();      // every read of act0 by the G phase is done
+            // ---- tanh transpose of layer 0, in place: act0 <- abar0
+#pragma unroll
+            for (int j = 0; j < TM; ++j) {
+                float2 hv[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) hv[c] = *reinterpret_cast<const float2*>(act0 + (j0 + j) * RS + c * TP + p0);
+                float h0[C], h1[C], o0[C], o1[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) { h0[c] = hv[c].x; h1[c] = hv[c].y; }
+                fast_tanh_jets_bwd<CF>(h0, acc[j][0], o0);
+                fast_tanh_jets_bwd<CF>(h1, acc[j][1], o1);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    *reinterpret_cast<float2*>(act0 + (j0 + j) * RS + c * TP + p0) = make_float2(o0[c], o1[c]);
+            }
+            __syncthreads();
+        }
+
+        // ---- first-layer gradients: rows j over warps, points over lanes --------------------------------
+        for (int j = warp; j < H; j += NW) {
+            float t0s = 0.0f, t1s = 0.0f, t2s = 0.0f, bs = 0.0f;
+            float ssl[NS > 0 ? NS : 1];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) ssl[s] = 0.0f;
+            for (int p = lane; p < TP; p += 32) {
+                const float a0 = act0[j * RS + p];
+                t0s = fmaf(a0, zs[p], t0s);
+                t1s = fmaf(a0, zs[TP + p], t1s);
+                t2s = fmaf(a0, zs[2 * TP + p], t2s);
+                bs += a0;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int c = s < NA2 ? 1 + 2 * s : 1 + 2 * NA2 + (s - NA2);
+                    ssl[s] += act0[j * RS + c * TP + p];
+                }
+            }
+            t0s = fbp_warp_sum(t0s); t1s = fbp_warp_sum(t1s); t2s = fbp_warp_sum(t2s); bs = fbp_warp_sum(bs);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) ssl[s] = fbp_warp_sum(ssl[s]);
+            if (lane == 0) {
+                gT[j] += t0s; gT[H + j] += t1s; gT[2 * H + j] += t2s; gB0[j] += bs;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) gS[s * H + j] += ssl[s];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write this work item's partial gradients -----------------------------------------------------------
+    float* gp = a.gpart + (int64_t)item * a.P;
+    int off = 0;
+    // W0 (H x xd) and b0
+    for (int i = tid; i < H * xd; i += NT) {
+        const int j = i / xd, d = i - j * xd;
+        float v = gT[d * H + j];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (a.axis[s] == d) v = fmaf(sel3(d, isd[0], isd[1], isd[2]), gS[s * H + j], v);
+        gp[i] = v;
+    }
+    for (int i = tid; i < H; i += NT) gp[H * xd + i] = gB0[i];
+    off = H * xd + H;
+    if constexpr (CF::NHID == 2) {
+        // reduce the register accumulators over the PG point groups through shared memory (reusing the activation
+        // buffers), one group per round in fixed order
+        static_assert(NQ * (JJ * KK + JJ) * 32 <= 2 * H * RS, "stage does not fit in the activation buffers");
+        float* stage = act0;                                   // [NQ][JJ*KK][32]
+        float* stageB = act0 + NQ * JJ * KK * 32;              // [NQ][JJ][32]
+        for (int g = 0; g < PG; ++g) {
+            if (pg == g) {
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+#pragma unroll
+                    for (int kk = 0; kk < KK; ++kk) {
+                        const int idx = (qd * JJ * KK + jj * KK + kk) * 32 + lane;
+                        stage[idx] = (g == 0 ? 0.0f : stage[idx]) + gacc[jj][kk];
+                    }
+                    const int ib = (qd * JJ + jj) * 32 + lane;
+                    stageB[ib] = (g == 0 ? 0.0f : stageB[ib]) + bacc[jj];
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < H * H; i += NT) {
+            const int j = i / H, k = i - j * H;
+            const int qj_ = j / HQ, jr = j % HQ, qk_ = k / HQ, kr = k % HQ;
+            const int ln = (jr & 3) * 8 + (kr & 7);
+            const int jj = jr >> 2, kk = kr >> 3;
+            const int q = qj_ * QW + qk_;
+            gp[off + i] = stage[(q * JJ * KK + jj * KK + kk) * 32 + ln];
+        }
+        off += H * H;
+        for (int j = tid; j < H; j += NT) {
+            const int qj_ = j / HQ, jr = j % HQ;
+            const int ln = (jr & 3) * 8;           // lane with kt == 0
+            const int q = qj_ * QW;                // quadrant with qk == 0
+            gp[off + j] = stageB[(q * JJ + (jr >> 2)) * 32 + ln];
+        }
+        off += H;
+    }
+    for (int i = tid; i < H; i += NT) gp[off + i] = gWL[i];
+    if (tid == 0) gp[off + H] = gBL[0];
+}
+
+// sums the partial gradients of every subdomain's work items in fixed order
+__global__ void fast_grad_reduce_kernel(const float* __restrict__ gpart, const int32_t* __restrict__ sub_item_off,
+                                        int m_active, int P, float* __restrict__ grads, int accumulate);
+
+// per-translation-unit launchers (one TU per hidden width, see fbp_fast_inst_*.cu)
+int fbp_fast_launch_h16(int nhid, int na2, int na1, bool backward, const FastArgs& a, int grid, cudaStream_t st);
+int fbp_fast_launch_h32(int nhid, int na2, int na1, bool backward, const FastArgs& a, int grid, cudaStream_t st);
+int fbp_fast_launch_h64(int nhid, int na2, int na1, bool backward, const FastArgs& a, int grid, cudaStream_t st);
+
+template <class CF>
+int fast_launch_one(bool backward, const FastArgs& a, int grid, cudaStream_t st) {
+    if (!backward) {
+        constexpr int TP = CF::TPF;
+        constexpr size_t bytes = sizeof(float) * CF::fwd_floats(TP);
+        static bool configured = false;
+        if (!configured) {
+            FBP_CHECK_CUDA(cudaFuncSetAttribute(fast_forward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            configured = true;
+        }
+        fast_forward_kernel<CF><<<grid, CF::NTF, bytes, st>>>(a);
+    } else {
+        constexpr int TP = CF::TPB;
+        constexpr size_t bytes = sizeof(float) * CF::bwd_floats(TP);
+        static bool configured = false;
+        if (!configured) {
+            FBP_CHECK_CUDA(cudaFuncSetAttribute(fast_backward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            configured = true;
+        }
+        fast_backward_kernel<CF><<<grid, CF::NTB, bytes, st>>>(a);
+    }
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+#define FBP_FAST_JET_SWITCH(H, NHID)                                                                        \
+    switch (na2 * 4 + na1) {                                                                                \
+        case 0: return fast_launch_one<FastCfg<H, NHID, 0, 0>>(backward, a, grid, st);                      \
+        case 1: return fast_launch_one<FastCfg<H, NHID, 0, 1>>(backward, a, grid, st);                      \
+        case 4: return fast_launch_one<FastCfg<H, NHID, 1, 0>>(backward, a, grid, st);                      \
+        case 5: return fast_launch_one<FastCfg<H, NHID, 1, 1>>(backward, a, grid, st);                      \
+        case 8: return fast_launch_one<FastCfg<H, NHID, 2, 0>>(backward, a, grid, st);                      \
+        case 12: return fast_launch_one<FastCfg<H, NHID, 3, 0>>(backward, a, grid, st);                     \
+        default: break;                                                                                     \
+    }

@@ -1,0 +1,9 @@
+// Instantiations of the tiled kernels for hidden width 16 (one translation unit per width to parallelise the build).
+#include "fbp_fast.cuh"
+
+int fbp_fast_launch_h16(int nhid, int na2, int na1, bool backward, const FastArgs& a, int grid, cudaStream_t st) {
+    if (nhid == 1) { FBP_FAST_JET_SWITCH(16, 1) }
+    else if (nhid == 2) { FBP_FAST_JET_SWITCH(16, 2) }
+    fbp_set_error("fbp_fast: no tiled instance for H=16 nhid=%d jets=(%d,%d)", nhid, na2, na1);
+    return 3;
+}

@@ -1,0 +1,184 @@
+"""GPU parity of the hot path against the oracle (float64 truth) on reduced variants of every BASELINE config:
+ujs (unconstrained and through the constraining operator), loss, parameter gradients, within the north-star
+tolerance of 1e-5 relative to each quantity's max magnitude (float32 arithmetic on the device)."""
+import numpy as np
+import pytest
+import torch
+
+from fbpinns_b200 import configs
+from fbpinns_b200.engine import subdomain_sum, unpack_params, Plan
+from fbpinns_b200.jets import JetSpec
+from fbpinns_b200.trainers import UpdateStep
+from fbpinns_b200.engine import PackedAdam
+import common
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5          # north star: u/ujs, loss and gradients within 1e-5 relative (fp32)
+NAMES = ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
+
+
+def _kernels_for(name):
+    return ["generic", "auto"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("kernel", ["generic", "auto"])
+def test_ujs_match_oracle(name, kernel):
+    import gpu_common
+    k = common.make_case(configs.CONFIGS[name](**configs.SMALL[name]), seed=0)
+    dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+    dev = params.device
+    all_params = _device_all_params(k, dev)
+    for ic, ev in enumerate(inp.evaluators):
+        jet = ev.plan.jet
+        if ev.takes.n == 0:
+            continue
+        ujets = ev.forward(params)
+        torch.cuda.synchronize()
+        ref_plain = common.oracle_ujs(k, ic, torch.float64, constrained=False)
+        for (iu, p), got, ref in zip(jet.required_ujs, gpu_common.ujets_columns(jet, ujets), ref_plain):
+            e = common.rel_err(got, ref[:, 0])
+            assert e < TOL, f"{name} constraint {ic} unconstrained d{p}: rel err {e:.2e}"
+        # through the constraining operator (host side, torch.func.jvp on the local Taylor model)
+        ref_con = common.oracle_ujs(k, ic, torch.float64, constrained=True)
+        ujs = jet.ujs_constrained(ujets, inp.constraints[ic][0], k.c.problem.constraining_fn, all_params)
+        for (iu, p), got, ref in zip(jet.required_ujs, ujs, ref_con):
+            e = common.rel_err(got.cpu().numpy(), ref)
+            assert e < TOL, f"{name} constraint {ic} constrained d{p}: rel err {e:.2e}"
+
+
+def _device_all_params(k, dev, prob_flat=None):
+    st = {}
+    for tag, d in k.all_params["static"].items():
+        if tag == "decomposition":
+            continue
+        st[tag] = {kk: (v.to(dev) if torch.is_tensor(v) else v) for kk, v in d.items()}
+    tr = {"problem": {kk: torch.as_tensor(v, device=dev) for kk, v in k.prob_trainable.items()}}
+    return {"static": st, "trainable": tr}
+
+
+def _make_step(k, inp, params, dev, graph=False):
+    all_params = _device_all_params(k, dev)
+    keys = list(k.prob_trainable.keys())
+    prob_flat = None
+    if keys:
+        prob_flat = torch.cat([torch.as_tensor(k.prob_trainable[kk], device=dev).reshape(-1) for kk in keys]).clone().requires_grad_(True)
+    adam = PackedAdam(k.m, params.shape[1], 0 if prob_flat is None else prob_flat.numel(), dev, learning_rate=1e-3)
+    step = UpdateStep(inp, params, adam, all_params, prob_flat, k.c.problem, use_cuda_graph=graph)
+    return step, adam, prob_flat
+
+
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("kernel", ["generic", "auto"])
+def test_loss_and_grads_match_oracle(name, kernel):
+    import gpu_common
+    k = common.make_case(configs.CONFIGS[name](**configs.SMALL[name]), seed=0)
+    dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+    dev = params.device
+    step, adam, prob_flat = _make_step(k, inp, params, dev)
+    step.grads.zero_()
+    loss = step.forward_loss()
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss, g_layers, g_prob = common.oracle_loss_and_grads(k, torch.float64)
+    assert abs(loss.item() - ref_loss) <= TOL * abs(ref_loss), f"loss {loss.item()} vs {ref_loss}"
+    plan = inp.evaluators[0].plan
+    got = unpack_params(plan, step.grads[:len(inp.active_ims)].contiguous())
+    for l, ((gw, gb), (rw, rb)) in enumerate(zip(got, g_layers)):
+        ew, eb = common.rel_err(gw.cpu().numpy(), rw), common.rel_err(gb.cpu().numpy(), rb)
+        assert ew < TOL and eb < TOL, f"{name} layer {l}: grad rel err W {ew:.2e} b {eb:.2e}"
+    if prob_flat is not None:
+        for i, kk in enumerate(k.prob_trainable):
+            e = common.rel_err(prob_flat.grad.cpu().numpy()[i], g_prob[kk])
+            assert e < TOL, f"problem param {kk}: {e:.2e}"
+
+
+def test_fixed_subdomains_get_no_gradient_and_values_match():
+    "active set with fixed (2) subdomains: forward uses them, reverse pass skips them (fbpinns/trainers.py:249-256, 292)"
+    import gpu_common
+    from fbpinns_b200.schedulers import LineSchedulerRectangularND
+    c = configs.cfg3_burgers(n_sub=(5, 5), n_pts=(40, 40), n_steps=40)
+    k0 = common.make_case(c, seed=0)
+    states = [a.copy() for a in LineSchedulerRectangularND(k0.all_params, 40, point=[0.], iaxis=0) if a is not None]
+    active = [a for a in states if (a == 2).any()][0]
+    k = common.make_case(c, seed=0, active=active)
+    for kernel in ["generic", "auto"]:
+        dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+        assert len(inp.fixed_ims) > 0
+        step, adam, _ = _make_step(k, inp, params, params.device)
+        step.grads.zero_()
+        loss = step.forward_loss()
+        loss.backward()
+        ref_loss, g_layers, _ = common.oracle_loss_and_grads(k, torch.float64)
+        assert abs(loss.item() - ref_loss) <= TOL * abs(ref_loss)
+        got = unpack_params(inp.evaluators[0].plan, step.grads[:len(inp.active_ims)].contiguous())
+        for (gw, gb), (rw, rb) in zip(got, g_layers):
+            assert common.rel_err(gw.cpu().numpy(), rw) < TOL and common.rel_err(gb.cpu().numpy(), rb) < TOL
+
+
+def test_mixed_derivative_generic_kernel():
+    "u_xy is outside the tiled family: the plan must fall back to the generic kernels and still match the oracle"
+    import gpu_common
+    from oracle import ref_model
+    c = configs.cfg5_poisson(n_sub=(4, 4), n_pts=(40, 40), layer_sizes=(2, 16, 1))
+    k = common.make_case(c, seed=3)
+    req = ((0, (0, 1)), (0, (1, 1)), (0, ()))
+    k.jets = [JetSpec(req, 2, 1)]
+    k.jmapss = [ref_model.get_jmaps(req)]
+    dd, inp, params = gpu_common.device_case(k, kernel="auto")
+    ev = inp.evaluators[0]
+    assert not ev.plan.is_fast
+    ujets = ev.forward(params)
+    ref = common.oracle_ujs(k, 0, torch.float64, constrained=False)
+    for (iu, p), got, r in zip(req, gpu_common.ujets_columns(ev.plan.jet, ujets), ref):
+        assert common.rel_err(got, r[:, 0]) < TOL, p
+
+
+def test_partition_of_unity_property_full_size():
+    """Size-independent property at BASELINE config 5's full size (64x64 subdomains, 1024x1024 points, where the
+    oracle is too slow): with every network constant (zero weights, last bias b) the windowed, normalised sum must
+    return u == b at every point and zero first/second derivatives (sum_i w_i / sum_i w_i == 1).  Also checks the
+    tiled kernels against the generic ones (two independent CUDA implementations) on random parameters."""
+    import gpu_common
+    c = configs.cfg5_poisson()
+    k = common.Case()
+    k.c = c
+    sd, _ = c.decomposition.init_params(**c.decomposition_init_kwargs)
+    sdom, _ = c.domain.init_params(**c.domain_init_kwargs)
+    sp, _ = c.problem.init_params(**c.problem_init_kwargs)
+    k.all_params = {"static": {"domain": sdom, "problem": sp, "decomposition": sd}, "trainable": {}}
+    k.m, k.xd, k.ud = sd["m"], 2, 1
+    k.layer_sizes = list(c.network_init_kwargs["layer_sizes"])
+    cons = c.problem.sample_constraints(k.all_params, c.domain, None, "grid", c.ns)
+    k.constraints_global = [[t.numpy() for t in cons[0][:-1]]]
+    k.x_batch_global = k.constraints_global[0][0]
+    k.offsets = np.array([0])
+    k.jets = [JetSpec(cons[0][-1], 2, 1)]
+    k.active = np.ones(k.m, dtype=int)
+    rng = np.random.default_rng(0)
+    from oracle import ref_model
+    k.layers = ref_model.init_fcn_params(rng, k.m, k.layer_sizes)
+    dd, inp, params = gpu_common.device_case(k, kernel="auto")
+    ev = inp.evaluators[0]
+    t = ev.takes
+    assert t.n == 1024 * 1024 and t.m_all == 4096 and t.s == 8726116
+    # constant networks
+    P = params.shape[1]
+    pc = torch.zeros_like(params)
+    pc[:, P - 1] = 0.75
+    u = ev.forward(pc)
+    torch.cuda.synchronize()
+    assert torch.allclose(u[:, 0], torch.full_like(u[:, 0], 0.75), atol=2e-6)
+    scale = (np.pi / (2.9 / 63 / 2)) ** 2          # magnitude of the window's second derivative
+    assert float(u[:, 1:].abs().max()) < 1e-5 * scale
+    # tiled vs generic on random parameters
+    u_fast = ev.forward(params).clone()
+    if ev.plan.is_fast:
+        from fbpinns_b200.engine import ConstraintEvaluator
+        gplan = Plan(k.layer_sizes, k.jets[0], kernel="generic")
+        gev = ConstraintEvaluator(gplan, t, ev.x, dd)
+        u_gen = gev.forward(params)
+        for c_ in range(u_gen.shape[1]):
+            e = common.rel_err(u_fast[:, c_].cpu().numpy(), u_gen[:, c_].cpu().numpy())
+            assert e < TOL, (c_, e)

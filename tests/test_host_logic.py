@@ -1,0 +1,178 @@
+"""CPU tests of the host-side logic (no GPU, no compute calls into the library)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_takes, ref_model
+from fbpinns_b200 import configs, decompositions, schedulers, _lib
+from fbpinns_b200.engine import build_work_items
+from fbpinns_b200.jets import JetSpec, get_ujs
+from fbpinns_b200.trainers import active_set_algebra
+from fbpinns_b200.constants import Constants, get_subdomain_ws
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    "the C-ABI library loads and exports every symbol include/fbpinn_b200.h declares (no compute calls)"
+    hdr = open(os.path.join(ROOT, "include", "fbpinn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fbp_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.fbp_version.restype = ctypes.c_int
+    assert lib.fbp_version() >= 100
+
+
+def test_plan_validation_without_gpu():
+    "plan creation is pure host code: closure / range errors are reported through fbp_last_error"
+    from fbpinns_b200.engine import Plan
+    p = Plan([2, 32, 32, 1], JetSpec(((0, (0, 0)), (0, (1, 1))), 2, 1))
+    assert p.P == 2 * 32 + 32 + 32 * 32 + 32 + 32 + 1 == 1185
+    with pytest.raises(NotImplementedError):
+        JetSpec(((0, (0, 0, 0)),), 2, 1)
+    with pytest.raises(_lib.FbpError):
+        Plan([3, 8, 1], JetSpec(((0, ()),), 2, 1))          # layer_sizes[0] != xd
+
+
+def test_no_cpu_fallback():
+    from fbpinns_b200.engine import pack_params, Plan
+    p = Plan([1, 4, 1], JetSpec(((0, ()),), 1, 1))
+    with pytest.raises(_lib.FbpError):
+        _lib.ptr(torch.zeros(3))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_decomposition_init_matches_oracle_bitwise(name):
+    c = configs.CONFIGS[name](**configs.SMALL[name])
+    sd, _ = c.decomposition.init_params(**c.decomposition_init_kwargs)
+    ref = ref_takes.rectangular_init_params(**c.decomposition_init_kwargs)
+    assert sd["m"] == ref["m"] and sd["xd"] == ref["xd"]
+    for a, b in zip(sd["subdomain"]["params"], ref["subdomain"]["params"]):
+        assert a.dtype == torch.float32 and np.array_equal(a.numpy(), b)
+    assert np.array_equal(sd["subdomain"]["pou"].numpy(), ref["subdomain"]["pou"])
+    assert np.array_equal(sd["xmins0"], ref["xmins0"]) and np.array_equal(sd["xmaxs0"], ref["xmaxs0"])
+
+
+def test_multilevel_and_non_overlapping():
+    xs1, xs2 = [np.linspace(0, 1, 3), np.linspace(0, 2, 4)], [np.linspace(0, 1, 5), np.linspace(0, 2, 6)]
+    kw = dict(subdomain_xss=[xs1, xs2], subdomain_wss=[get_subdomain_ws(xs1, 2.2), get_subdomain_ws(xs2, 2.2)], unnorm=(0., 2.))
+    sd, _ = decompositions.MultilevelRectangularDecompositionND.init_params(**kw)
+    ref = ref_takes.multilevel_init_params(**kw)
+    assert sd["m"] == 12 + 30 == ref["m"]
+    for a, b in zip(sd["subdomain"]["params"], ref["subdomain"]["params"]):
+        assert np.array_equal(a.numpy(), b)
+    assert np.array_equal(sd["subdomain"]["pou"].numpy(), ref["subdomain"]["pou"])
+    with pytest.raises(ValueError):
+        decompositions.RectangularDecompositionND.init_params([np.linspace(0, 1, 5)], [0.1 * np.ones(5)], (0., 1.))
+
+
+def test_active_set_algebra_matches_oracle_get_inputs():
+    rng = np.random.default_rng(0)
+    c = configs.cfg3_burgers(n_sub=(5, 4), n_pts=(30, 30))
+    decomp = ref_takes.rectangular_init_params(**c.decomposition_init_kwargs)
+    m = decomp["m"]
+    x = rng.uniform([-1, 0], [0.2, 0.5], size=(400, 2)).astype(np.float32)      # leaves some models without points
+    for trial in range(5):
+        active = rng.integers(0, 3, size=m)
+        takes, all_ims, a_ims, f_ims, act = ref_takes.get_inputs(x, active, decomp)
+        counts = ref_takes.inside_mask(decomp, x, np.arange(m)).sum(0)
+        act2, a2, f2, all2, pos = active_set_algebra(active, counts)
+        assert np.array_equal(act, act2) and np.array_equal(a_ims, a2) and np.array_equal(f_ims, f2)
+        assert np.array_equal(all_ims, all2)
+        assert (pos[all2] == np.arange(len(all2))).all() and (np.delete(pos, all2) == -1).all()
+
+
+def test_schedulers_against_golden():
+    "golden vectors produced by the reference's own fbpinns/schedulers.py (tests/golden/make_golden.py)"
+    path = os.path.join(ROOT, "tests", "golden", "schedulers.npz")
+    g = np.load(path, allow_pickle=True)
+    c = configs.cfg3_burgers(n_sub=(6, 5), n_pts=(10, 10))
+    sd, _ = c.decomposition.init_params(**c.decomposition_init_kwargs)
+    ap = {"static": {"decomposition": sd}}
+    runs = {
+        "line": schedulers.LineSchedulerRectangularND(ap, 50, point=[0.], iaxis=0),
+        "point": schedulers.PointSchedulerRectangularND(ap, 37, point=[0.3, 0.1]),
+        "all": schedulers.AllActiveSchedulerND(ap, 5),
+    }
+    for name, sch in runs.items():
+        steps = g[name + "_steps"]
+        states = g[name + "_states"]
+        got_steps, got_states = [], []
+        for i, a in enumerate(sch):
+            if a is not None:
+                got_steps.append(i)
+                got_states.append(np.array(a).copy())
+        assert np.array_equal(np.array(got_steps), steps), name
+        assert np.array_equal(np.array(got_states), states), name
+    c3 = configs.cfg4_wave3d(n_sub=(3, 4, 5), n_pts=(4, 4, 4))
+    sd3, _ = c3.decomposition.init_params(**c3.decomposition_init_kwargs)
+    sch = schedulers.PlaneSchedulerRectangularND({"static": {"decomposition": sd3}}, 30, point=[0.], iaxes=[0, 1])
+    got = [(i, np.array(a).copy()) for i, a in enumerate(sch) if a is not None]
+    assert np.array_equal(np.array([i for i, _ in got]), g["plane_steps"])
+    assert np.array_equal(np.array([a for _, a in got]), g["plane_states"])
+
+
+def test_constraining_jets_by_local_taylor_model():
+    "ujs of constraining_fn(x, u(x)) from the jets of u: exact against nested jvp through an analytic u"
+    from fbpinns_b200.problems import BurgersEquation2D, WaveEquationConstantVelocity3D
+    torch.manual_seed(0)
+    for prob, xd, req in [(BurgersEquation2D, 2, ((0, ()), (0, (0,)), (0, (1,)), (0, (0, 0)))),
+                          (WaveEquationConstantVelocity3D, 3, ((0, (0, 0)), (0, (1, 1)), (0, (2, 2))))]:
+        sp, _ = prob.init_params()
+        ap = {"static": {"problem": {k: (v.double() if torch.is_tensor(v) else v) for k, v in sp.items()}}, "trainable": {}}
+        x = torch.rand(17, xd, dtype=torch.float64) * 0.8 + 0.1
+        A = torch.randn(xd, dtype=torch.float64)
+
+        def u_of(x):
+            return torch.sin(x @ A).unsqueeze(1) + (x ** 2).sum(1, keepdim=True)
+        jet = JetSpec(req, xd, 1)
+        # analytic jets of u
+        cols = []
+        s_, c_ = torch.sin(x @ A), torch.cos(x @ A)
+        for p in jet.comps:
+            if len(p) == 0:
+                cols.append(s_ + (x ** 2).sum(1))
+            elif len(p) == 1:
+                cols.append(c_ * A[p[0]] + 2 * x[:, p[0]])
+            else:
+                cols.append(-s_ * A[p[0]] * A[p[1]] + (2.0 if p[0] == p[1] else 0.0))
+        ujets = torch.stack(cols, 1)
+        got = jet.ujs_constrained(ujets, x, prob.constraining_fn, ap)
+        ref = get_ujs(x, jet.jmaps, lambda xx: (prob.constraining_fn(ap, xx, u_of(xx)), ()))
+        for a, b in zip(got, ref):
+            assert torch.allclose(a, b, rtol=1e-10, atol=1e-10)
+
+
+def test_work_items_cover_all_pairs():
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 3000, size=50)
+    sub_off = np.concatenate([[0], np.cumsum(counts)])
+    for tile, target in [(128, 1184), (64, 10), (128, 1)]:
+        items, sio, nia = build_work_items(sub_off, 30, tile, target)
+        assert items[:, 2].sum() == sub_off[-1]
+        for sp in range(50):
+            it = items[sio[sp]:sio[sp + 1]]
+            assert (it[:, 0] == sp).all()
+            if len(it):
+                assert it[0, 1] == sub_off[sp] and it[-1, 1] + it[-1, 2] == sub_off[sp + 1]
+                assert (it[:-1, 2] % tile == 0).all()
+                assert np.array_equal(it[:, 3], np.arange(len(it)))
+        assert nia == sio[30]
+
+
+def test_constants_reject_unknown_keys():
+    with pytest.raises(KeyError):
+        Constants(not_a_key=1)
+    c = Constants(seed=3)
+    assert c.seed == 3 and c["n_steps"] == 15000
