@@ -46,6 +46,7 @@ _I32, _I64, _F = C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "fbp_last_error": (C.c_char_p, []),
     "fbp_version": (C.c_int, []),
+    "fbp_launch_count": (_I64, []),
     "fbp_device_info": (C.c_int, [C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I64)]),
     "fbp_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(PlanDesc)]),
     "fbp_plan_destroy": (C.c_int, [_P]),

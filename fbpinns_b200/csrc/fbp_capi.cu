@@ -5,7 +5,12 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void fbp_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void fbp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -19,6 +24,8 @@ extern "C" {
 const char* fbp_last_error(void) { return g_err; }
 
 int fbp_version(void) { return 100; }
+
+int64_t fbp_launch_count(void) { return (int64_t)g_launches.load(); }
 
 int fbp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_per_block_optin) {
     int dev = 0;

@@ -14,6 +14,7 @@
 // error handling (thread-local message, never throws across the C ABI)
 // ---------------------------------------------------------------------------------------------------
 void fbp_set_error(const char* fmt, ...);
+void fbp_count_launch();   // every kernel launch of this library is counted (fbp_launch_count)
 
 #define FBP_CHECK_CUDA(expr)                                                                        \
     do {                                                                                            \
@@ -34,6 +35,7 @@ void fbp_set_error(const char* fmt, ...);
 
 #define FBP_LAUNCH_CHECK()                                                                          \
     do {                                                                                            \
+        fbp_count_launch();                                                                         \
         cudaError_t _e = cudaGetLastError();                                                        \
         if (_e != cudaSuccess) {                                                                    \
             fbp_set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \

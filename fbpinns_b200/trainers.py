@@ -173,10 +173,13 @@ class UpdateStep:
             if self.prob_flat is not None:
                 self.prob_flat.grad = None
             self.hook.grad = None
+            from . import _lib
+            n0 = _lib.load().fbp_launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._eager()
             self.graph = g
+            self.kernel_launches_per_step = int(_lib.load().fbp_launch_count() - n0)
         self.graph.replay()
         return self.loss_out
 
@@ -230,19 +233,18 @@ class FBPINNTrainer(_Trainer):
             all_params["trainable"]["network"] = {"subdomain": ps_[1]}
         return all_params, dev
 
-    def train(self):
-        "Train model"
+    def setup(self):
+        """Everything train() does before its loop (fbpinns/trainers.py:580-624): parameters, constraints, jet specs,
+        packed parameter / Adam buffers, test points.  Public so that single steps can be driven from outside
+        (bench.py, notebooks): setup() -> set_active(active) -> step() ..."""
         c = self.c
         np.random.seed(c.seed)
         all_params, dev = self._init_all_params()
         domain, problem, decomposition = c.domain, c.problem, c.decomposition
         m = all_params["static"]["decomposition"]["m"]
         ud, xd = all_params["static"]["problem"]["dims"]
-        layer_sizes = list(c.network_init_kwargs["layer_sizes"])
-        dd = decomposition._device(all_params, dev)
-
-        # scheduler
-        scheduler = c.scheduler(all_params=all_params, n_steps=c.n_steps, **c.scheduler_kwargs)
+        self.layer_sizes = list(c.network_init_kwargs["layer_sizes"])
+        self.dd = decomposition._device(all_params, dev)
 
         # constraints (fbpinns/trainers.py:436-461)
         key = np.random.default_rng(c.seed + 1)
@@ -252,73 +254,96 @@ class FBPINNTrainer(_Trainer):
             for c_ in con[:-1]:
                 assert c_.shape[0] == con[0].shape[0]
         required_ujss = [con[-1] for con in constraints_global]
-        constraints_global = [[t.to(dev, torch.float32).contiguous() for t in con[:-1]] for con in constraints_global]
-        x_batch_global = torch.cat([con[0] for con in constraints_global]).contiguous()
-        sizes = [con[0].shape[0] for con in constraints_global]
-        constraint_offsets = np.cumsum([0] + sizes[:-1]).astype(np.int64)
-        jets = [JetSpec(r, xd, ud) for r in required_ujss]
-        logger.info(f"Total number of constraints: {len(constraints_global)}")
+        self.constraints_global = [[t.to(dev, torch.float32).contiguous() for t in con[:-1]] for con in constraints_global]
+        self.x_batch_global = torch.cat([con[0] for con in self.constraints_global]).contiguous()
+        sizes = [con[0].shape[0] for con in self.constraints_global]
+        self.constraint_offsets = np.cumsum([0] + sizes[:-1]).astype(np.int64)
+        self.jets = [JetSpec(r, xd, ud) for r in required_ujss]
+        logger.info(f"Total number of constraints: {len(self.constraints_global)}")
 
         # packed parameters + problem trainables + Adam
-        value_plan = Plan(layer_sizes, JetSpec(tuple((iu, ()) for iu in range(ud)), xd, ud), kernel=c.kernel)
+        self.value_plan = Plan(self.layer_sizes, JetSpec(tuple((iu, ()) for iu in range(ud)), xd, ud), kernel=c.kernel)
         layers = [(w.to(dev), b.to(dev)) for w, b in all_params["trainable"]["network"]["subdomain"]["layers"]]
-        params = pack_params(value_plan, layers)
+        self.params = pack_params(self.value_plan, layers)
         prob_tr = all_params["trainable"].get("problem", {})
         prob_keys = list(prob_tr.keys())
         if prob_keys:
             flat = torch.cat([prob_tr[k].reshape(-1).float() for k in prob_keys]).to(dev)
-            prob_flat = flat.clone().requires_grad_(True)
+            self.prob_flat = flat.clone().requires_grad_(True)
             off = 0
             for k in prob_keys:
                 nel = prob_tr[k].numel()
-                all_params["trainable"]["problem"][k] = prob_flat[off:off + nel].view(prob_tr[k].shape)
+                all_params["trainable"]["problem"][k] = self.prob_flat[off:off + nel].view(prob_tr[k].shape)
                 off += nel
         else:
-            prob_flat = None
+            self.prob_flat = None
         for tag in ("domain", "problem"):
             st = all_params["static"].get(tag, {})
             for k, v in st.items():
                 if torch.is_tensor(v):
                     st[k] = v.to(dev)
-        adam = PackedAdam(m, value_plan.P, 0 if prob_flat is None else prob_flat.numel(), dev, **c.optimiser_kwargs)
-        logger.info(f"Total number of trainable parameters: network: {params.numel():,}")
+        self.adam = PackedAdam(m, self.value_plan.P, 0 if self.prob_flat is None else self.prob_flat.numel(), dev,
+                               **c.optimiser_kwargs)
+        logger.info(f"Total number of trainable parameters: network: {self.params.numel():,}")
 
         # test data (fbpinns/trainers.py:463-470, 620-624)
-        x_batch_test = domain.sample_interior(all_params=all_params, key=None, sampler="grid", batch_shape=c.n_test)
-        x_batch_test = x_batch_test.to(dev)
+        self.x_batch_test = domain.sample_interior(all_params=all_params, key=None, sampler="grid",
+                                                   batch_shape=c.n_test).to(dev)
         try:
-            u_exact = problem.exact_solution(all_params=all_params, x_batch=x_batch_test, batch_shape=c.n_test)
+            self.u_exact = problem.exact_solution(all_params=all_params, x_batch=self.x_batch_test, batch_shape=c.n_test)
         except NotImplementedError:
-            u_exact = None
+            self.u_exact = None
         self._test_eval = None
+        self.all_params = all_params
+        self.n_rebuilds = 0
+        self.inputs = self.update = None
+        return self
 
-        self.all_params, self.params, self.adam, self.dd, self.value_plan = all_params, params, adam, dd, value_plan
-        self.prob_flat = prob_flat
+    def set_active(self, active, i=0):
+        "Active-set change (fbpinns/trainers.py:634-653): rebuild the update inputs on the device; no compilation."
+        c = self.c
+        t0 = time.time()
+        logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs..")
+        self.inputs = get_update_inputs(active, self.all_params, self.dd, self.x_batch_global, self.constraints_global,
+                                        self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel)
+        self.update = UpdateStep(self.inputs, self.params, self.adam, self.all_params, self.prob_flat, c.problem,
+                                 c.use_cuda_graph)
+        self.n_rebuilds += 1
+        torch.cuda.synchronize()
+        logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs done ({time.time() - t0:.2f} s); "
+                    f"average points/dimension in active subdomains: {self.inputs.d:.2f}")
+        return self.inputs
+
+    def step(self):
+        "One FBPINN_update on the current active set; returns the device scalar loss (no host sync)."
+        return self.update()
+
+    def step_from_host(self, x_host_pinned_list):
+        """End-to-end step: copies each constraint's collocation points from (pinned) host memory into the device
+        buffers the kernels read, runs one update and returns the loss as a python float (device->host read)."""
+        for con, xh in zip(self.inputs.constraints, x_host_pinned_list):
+            con[0].copy_(xh, non_blocking=True)
+        return float(self.update().item())
+
+    def train(self):
+        "Train model"
+        c = self.c
+        self.setup()
+        scheduler = c.scheduler(all_params=self.all_params, n_steps=c.n_steps, **c.scheduler_kwargs)
 
         # train loop (fbpinns/trainers.py:626-677)
         u_test_losses = []
         start0, start1, report_time = time.time(), time.time(), 0.
-        step = None
         lossval = None
-        self.n_rebuilds = 0
         for i, active_ in enumerate(scheduler):
             if active_ is not None:
-                t0 = time.time()
-                logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs..")
-                inputs = get_update_inputs(active_, all_params, dd, x_batch_global, constraints_global,
-                                           constraint_offsets, jets, layer_sizes, kernel=c.kernel)
-                step = UpdateStep(inputs, params, adam, all_params, prob_flat, problem, c.use_cuda_graph)
-                self.n_rebuilds += 1
-                torch.cuda.synchronize()
-                logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs done ({time.time() - t0:.2f} s); "
-                            f"average points/dimension in active subdomains: {inputs.d:.2f}")
-                self.inputs, self.step = inputs, step
+                self.set_active(active_, i)
             if i == 0:
                 u_test_losses, start1, report_time = self._report(
-                    i, u_test_losses, start0, start1, report_time, u_exact, x_batch_test, lossval)
-            lossval = step()
+                    i, u_test_losses, start0, start1, report_time, self.u_exact, self.x_batch_test, lossval)
+            lossval = self.step()
             u_test_losses, start1, report_time = self._report(
-                i + 1, u_test_losses, start0, start1, report_time, u_exact, x_batch_test, lossval)
+                i + 1, u_test_losses, start0, start1, report_time, self.u_exact, self.x_batch_test, lossval)
 
         torch.cuda.synchronize()
         logger.info(f"[i: {c.n_steps}/{c.n_steps}] Training complete")

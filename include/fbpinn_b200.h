@@ -96,6 +96,8 @@ typedef struct fbp_takes_view {
 /* ---- errors / info ---------------------------------------------------------------------------- */
 const char* fbp_last_error(void);
 int fbp_version(void);
+/* Number of kernels this library has launched (or recorded into a CUDA graph being captured) so far. */
+int64_t fbp_launch_count(void);
 /* Device properties the host uses for grid sizing. Fails if no CUDA device / not sm_100. */
 int fbp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_per_block_optin);
 

@@ -176,3 +176,22 @@ def test_constants_reject_unknown_keys():
         Constants(not_a_key=1)
     c = Constants(seed=3)
     assert c.seed == 3 and c["n_steps"] == 15000
+
+
+def test_every_baseline_config_has_a_tiled_kernel_instance():
+    "the five BASELINE configs (true layer sizes, true jet sets) must run on the tiled family, not the generic fallback"
+    from fbpinns_b200.engine import Plan
+    import common
+    for name, fn in configs.CONFIGS.items():
+        c = fn()
+        sp, _ = c.problem.init_params(**c.problem_init_kwargs)
+        ud, xd = sp["dims"]
+        small = common.make_case(configs.CONFIGS[name](**configs.SMALL[name]), seed=0)
+        for req in small.required_ujss:
+            p = Plan(c.network_init_kwargs["layer_sizes"], JetSpec(req, xd, ud))
+            assert p.is_fast, (name, req)
+        assert Plan(c.network_init_kwargs["layer_sizes"], JetSpec(((0, ()),), xd, ud)).is_fast
+    for ls in ([2, 32, 1], [2, 64, 64, 1]):                       # the sweep networks of config 5
+        assert Plan(ls, JetSpec(((0, (0, 0)), (0, (1, 1))), 2, 1)).is_fast
+    assert not Plan([2, 24, 1], JetSpec(((0, ()),), 2, 1)).is_fast     # falls back to the generic family
+    assert not Plan([2, 32, 32, 32, 1], JetSpec(((0, ()),), 2, 1)).is_fast
