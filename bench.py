@@ -183,6 +183,7 @@ def run_ours(args):
     m = tr.dd.m
     tr.set_active(np.ones(m, dtype=int))
     ev = tr.inputs.evaluators[0]
+    ev = ev.ev if hasattr(ev, "ev") else ev          # sharded evaluators wrap the local one
     takes = tr.inputs.takess[0]
     C = ev.plan.jet.C
     n_points_global = int(np.prod(kw["n_pts"]))
@@ -223,7 +224,7 @@ def run_ours(args):
     steps_per_s = 1e3 / ms_per_step
 
     # ---- end to end: host (pinned) points -> device, step, loss -> host, through the public API -------------------
-    x_host = [con[0].detach().cpu().pin_memory() for con in tr.inputs.constraints]
+    x_host = [b.detach().cpu().pin_memory() for b in tr.point_buffers()]
     h2d = int(sum(x.numel() * 4 for x in x_host))
     for _ in range(3):
         tr.step_from_host(x_host)

@@ -41,7 +41,24 @@ window_sums_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ x, c
     for (int c = 0; c < pd.C; ++c) dsum[r * pd.C + c] = acc[c];
 }
 
+// ---- row sums: nsum[r] = sum of the row's pair jets in REFERENCE order (exposed for the multi-GPU halo step) ----
+__global__ void __launch_bounds__(RT)
+row_sums_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_out, float* __restrict__ nsum) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= tv.q) return;
+    const int V = pd.C * pd.ud;
+    float N[FBP_MAX_COMP * FBP_MAX_UD];
+    for (int v = 0; v < V; ++v) N[v] = 0.0f;
+    for (int j = tv.d_row_off[r]; j < tv.d_row_off[r + 1]; ++j) {
+        const float* po = pair_out + (int64_t)tv.d_pos[j] * V;
+        for (int v = 0; v < V; ++v) N[v] += po[v];
+    }
+    for (int v = 0; v < V; ++v) nsum[r * V + v] = N[v];
+}
+
 // ---- forward: ujets[p] = (1/npou) sum_rows quotient_jets( sum_pairs N , D ) -------------------------
+// FROM_ROWS = false: N is summed here from the pair jets; true: N is read from precomputed row sums.
+template <bool FROM_ROWS>
 __global__ void __launch_bounds__(RT)
 reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_out,
                       const float* __restrict__ dsum, float* __restrict__ ujets) {
@@ -52,10 +69,14 @@ reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ p
     for (int v = 0; v < V; ++v) acc[v] = 0.0f;
     for (int r = tv.d_pt_row_off[p]; r < tv.d_pt_row_off[p + 1]; ++r) {
         float N[FBP_MAX_COMP * FBP_MAX_UD];
-        for (int v = 0; v < V; ++v) N[v] = 0.0f;
-        for (int j = tv.d_row_off[r]; j < tv.d_row_off[r + 1]; ++j) {
-            const float* po = pair_out + (int64_t)tv.d_pos[j] * V;
-            for (int v = 0; v < V; ++v) N[v] += po[v];
+        if (FROM_ROWS) {
+            for (int v = 0; v < V; ++v) N[v] = pair_out[(int64_t)r * V + v];
+        } else {
+            for (int v = 0; v < V; ++v) N[v] = 0.0f;
+            for (int j = tv.d_row_off[r]; j < tv.d_row_off[r + 1]; ++j) {
+                const float* po = pair_out + (int64_t)tv.d_pos[j] * V;
+                for (int v = 0; v < V; ++v) N[v] += po[v];
+            }
         }
         float D[FBP_MAX_COMP];
         for (int c = 0; c < C; ++c) D[c] = dsum[(int64_t)r * C + c];
@@ -195,7 +216,24 @@ int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const flo
                        float* d_ujets, void* stream) {
     FBP_REQUIRE(plan && tv, "fbp_reduce_forward: null plan/takes");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_ujets);
+    reduce_forward_kernel<false><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_ujets);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+int fbp_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out, float* d_nsum, void* stream) {
+    FBP_REQUIRE(plan && tv, "fbp_row_sums: null plan/takes");
+    if (tv->q == 0) return 0;
+    row_sums_kernel<<<blocks_for(tv->q, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_nsum);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_nsum, const float* d_dsum,
+                            float* d_ujets, void* stream) {
+    FBP_REQUIRE(plan && tv, "fbp_reduce_rows_forward: null plan/takes");
+    if (tv->n == 0) return 0;
+    reduce_forward_kernel<true><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_nsum, d_dsum, d_ujets);
     FBP_LAUNCH_CHECK();
     return 0;
 }

@@ -32,17 +32,20 @@ __device__ __forceinline__ bool inside_box(const float* s_box, int b, const floa
     return in;
 }
 
+// A model whose position is < 0 (not in all_ims: discarded, or owned by another rank) is staged as an empty box
+// (lo = +inf, hi = -inf) so that it never matches.
 template <int XD>
 __device__ __forceinline__ void stage_boxes(float* s_box, int32_t* s_aux, const float* __restrict__ sub_static,
                                             const int32_t* __restrict__ models, const int32_t* __restrict__ aux,
-                                            int b0, int nb, int ss) {
+                                            const int32_t* __restrict__ pos, int b0, int nb, int ss) {
     for (int t = threadIdx.x; t < nb; t += blockDim.x) {
         int im = models ? models[b0 + t] : b0 + t;
         const float* rec = sub_static + (int64_t)im * ss;
+        const bool keep = pos ? pos[im] >= 0 : true;
 #pragma unroll
         for (int d = 0; d < XD; ++d) {
-            s_box[(2 * d) * BOX_CHUNK + t] = rec[d];
-            s_box[(2 * d + 1) * BOX_CHUNK + t] = rec[XD + d];
+            s_box[(2 * d) * BOX_CHUNK + t] = keep ? rec[d] : INFINITY;
+            s_box[(2 * d + 1) * BOX_CHUNK + t] = keep ? rec[XD + d] : -INFINITY;
         }
         if (s_aux) s_aux[t] = aux ? aux[im] : 0;
     }
@@ -54,7 +57,7 @@ template <int XD>
 __global__ void __launch_bounds__(TT)
 inside_count_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ sub_static, int ss,
                     const int32_t* __restrict__ models, int n_models, const int32_t* __restrict__ pou,
-                    int32_t* __restrict__ pt_count, int32_t* __restrict__ pt_rows, int32_t* __restrict__ model_count) {
+                    const int32_t* __restrict__ pos, int32_t* __restrict__ pt_count, int32_t* __restrict__ pt_rows, int32_t* __restrict__ model_count) {
     __shared__ float s_box[2 * XD * BOX_CHUNK];
     __shared__ int32_t s_pou[BOX_CHUNK];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,7 +68,7 @@ inside_count_kernel(const float* __restrict__ x, int64_t n, const float* __restr
     for (int b0 = 0; b0 < n_models; b0 += BOX_CHUNK) {
         int nb = min(BOX_CHUNK, n_models - b0);
         __syncthreads();
-        stage_boxes<XD>(s_box, pou ? s_pou : nullptr, sub_static, models, pou, b0, nb, ss);
+        stage_boxes<XD>(s_box, pou ? s_pou : nullptr, sub_static, models, pou, pos, b0, nb, ss);
         __syncthreads();
         if (i < n) {
             for (int b = 0; b < nb; ++b) {
@@ -106,7 +109,7 @@ takes_fill_kernel(const float* __restrict__ x, int64_t n, const float* __restric
     for (int b0 = 0; b0 < m; b0 += BOX_CHUNK) {
         int nb = min(BOX_CHUNK, m - b0);
         __syncthreads();
-        stage_boxes<XD>(s_box, s_pou, sub_static, nullptr, pou, b0, nb, ss);
+        stage_boxes<XD>(s_box, s_pou, sub_static, nullptr, pou, pos_of_model, b0, nb, ss);
         __syncthreads();
         if (i < n) {
             for (int b = 0; b < nb; ++b) {
@@ -172,9 +175,9 @@ int exclusive_scan_i32(const int32_t* d_in, int32_t* d_out, int64_t n, cudaStrea
 
 template <int XD>
 int launch_count(const float* d_x, int64_t n, const float* d_sub_static, const int32_t* d_models, int n_models,
-                 const int32_t* d_pou, int32_t* d_pt_count, int32_t* d_pt_rows, int32_t* d_model_count,
-                 cudaStream_t st) {
-    inside_count_kernel<XD><<<nblk(n, TT), TT, 0, st>>>(d_x, n, d_sub_static, 2 * XD + 3, d_models, n_models, d_pou,
+                 const int32_t* d_pou, const int32_t* d_pos, int32_t* d_pt_count, int32_t* d_pt_rows,
+                 int32_t* d_model_count, cudaStream_t st) {
+    inside_count_kernel<XD><<<nblk(n, TT), TT, 0, st>>>(d_x, n, d_sub_static, 2 * XD + 3, d_models, n_models, d_pou, d_pos,
                                                         d_pt_count, d_pt_rows, d_model_count);
     FBP_LAUNCH_CHECK();
     return 0;
@@ -207,9 +210,9 @@ int fbp_inside_count(const float* d_x, int64_t n, int32_t xd, const float* d_sub
         FBP_CHECK_CUDA(cudaMemsetAsync(d_model_count, 0, sizeof(int32_t) * n_models, st));
     if (n == 0) return 0;
     switch (xd) {
-        case 1: return launch_count<1>(d_x, n, d_sub_static, d_models, n_models, nullptr, d_pt_count, nullptr, d_model_count, st);
-        case 2: return launch_count<2>(d_x, n, d_sub_static, d_models, n_models, nullptr, d_pt_count, nullptr, d_model_count, st);
-        default: return launch_count<3>(d_x, n, d_sub_static, d_models, n_models, nullptr, d_pt_count, nullptr, d_model_count, st);
+        case 1: return launch_count<1>(d_x, n, d_sub_static, d_models, n_models, nullptr, nullptr, d_pt_count, nullptr, d_model_count, st);
+        case 2: return launch_count<2>(d_x, n, d_sub_static, d_models, n_models, nullptr, nullptr, d_pt_count, nullptr, d_model_count, st);
+        default: return launch_count<3>(d_x, n, d_sub_static, d_models, n_models, nullptr, nullptr, d_pt_count, nullptr, d_model_count, st);
     }
 }
 
@@ -266,9 +269,9 @@ int fbp_takes_begin(fbp_takes_builder** out, const float* d_x, int64_t n, int32_
     FBP_CHECK_CUDA(cudaMemsetAsync(d_rows + n, 0, sizeof(int32_t), st));
     int rc;
     switch (xd) {
-        case 1: rc = launch_count<1>(d_x, n, d_sub_static, nullptr, m, d_pou_of_model, d_cnt, d_rows, nullptr, st); break;
-        case 2: rc = launch_count<2>(d_x, n, d_sub_static, nullptr, m, d_pou_of_model, d_cnt, d_rows, nullptr, st); break;
-        default: rc = launch_count<3>(d_x, n, d_sub_static, nullptr, m, d_pou_of_model, d_cnt, d_rows, nullptr, st); break;
+        case 1: rc = launch_count<1>(d_x, n, d_sub_static, nullptr, m, d_pou_of_model, d_pos_of_model, d_cnt, d_rows, nullptr, st); break;
+        case 2: rc = launch_count<2>(d_x, n, d_sub_static, nullptr, m, d_pou_of_model, d_pos_of_model, d_cnt, d_rows, nullptr, st); break;
+        default: rc = launch_count<3>(d_x, n, d_sub_static, nullptr, m, d_pou_of_model, d_pos_of_model, d_cnt, d_rows, nullptr, st); break;
     }
     if (rc == 0) rc = exclusive_scan_i32(d_cnt, b->d_pt_off, n + 1, st);
     if (rc == 0) rc = exclusive_scan_i32(d_rows, b->d_pt_row_off, n + 1, st);

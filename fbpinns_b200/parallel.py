@@ -1,0 +1,285 @@
+"""
+Multi-GPU sharding of the FBPINN step: one process per GPU, subdomains partitioned into contiguous
+blocks of the global subdomain index (= slabs of grid rows along dimension 0, fbpinns/decompositions.py:163).
+
+  * network parameters, their gradients and Adam state are purely local to the owning rank — no weight all-reduce;
+  * every collocation point is OWNED by the rank holding the lowest-index subdomain that contains it; the owner
+    evaluates the quotient rule, the constraining operator and the loss for it;
+  * a point that also lies inside subdomains of another rank (the overlap strip between two slabs) receives that
+    rank's partial numerator sums in the forward pass and sends back the cotangent of the row in the reverse pass:
+    ONE all_to_all_single per direction per constraint (NCCL over NVLink/NVSwitch; gloo in the CPU tests), the
+    denominators D are exchanged once per active-set change;
+  * the scalar loss and the gradients of the problem's own trainables are all-reduced.
+
+`loss_fn` must be a sum of per-constraint means (true for every reference problem): rank r scales the cotangents of
+constraint ic by n_owned(r, ic) / n(ic).  Gradients of the network parameters are then exact; gradients of the
+problem's own trainables and the reported loss use the weights of the first constraint (exact for single-constraint
+problems and whenever those quantities depend on one constraint only).
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ptr, stream_ptr, check
+from .engine import Plan, DeviceTakes, ConstraintEvaluator, gather_rows, nonzero_i32
+
+
+class Shard:
+    def __init__(self, rank, world, group=None):
+        self.rank, self.world, self.group = int(rank), int(world), group
+
+    def block(self, m, j=None):
+        "contiguous block [lo, hi) of global subdomain indices owned by rank j"
+        j = self.rank if j is None else j
+        return (j * m) // self.world, ((j + 1) * m) // self.world
+
+
+def shard_trainer(trainer, rank, world, group=None):
+    trainer.shard = Shard(rank, world, group)
+    return trainer
+
+
+# --------------------------------------------------------------------------------------------------- halo bookkeeping (pure index logic)
+
+def build_halo_lists(inside, rank):
+    """inside: (world, n) bool — inside[j, p] = point p lies in >= 1 subdomain of rank j (of the current all_ims).
+    Returns dict with
+      local_ips   ascending indices of the points this rank evaluates (inside[rank])
+      owner       (n,) owning rank of every point (lowest rank containing it, -1 if none)
+      owned_local bool over local points: this rank owns the point
+      send[j]     local indices whose owner is j (this rank sends its partial sums for them to j)
+      recv[j]     local indices owned here that rank j also touches (partials arrive from j)
+    send[j] on rank r and recv[r] on rank j enumerate the same points in the same (ascending global) order."""
+    inside = np.asarray(inside, dtype=bool)
+    world, n = inside.shape
+    covered = inside.any(0)
+    owner = np.where(covered, inside.argmax(0), -1)
+    local_ips = np.nonzero(inside[rank])[0]
+    own_l = owner[local_ips] == rank
+    send, recv = {}, {}
+    for j in range(world):
+        if j == rank:
+            continue
+        send[j] = np.nonzero(owner[local_ips] == j)[0]
+        recv[j] = np.nonzero(own_l & inside[j][local_ips])[0]
+    return dict(local_ips=local_ips, owner=owner, owned_local=own_l, send=send, recv=recv)
+
+
+class HaloExchange:
+    """Row exchange for one constraint: forward adds the partial sums of shared rows into their owner,
+    reverse returns the owner's row cotangents to the sharers."""
+
+    def __init__(self, halo, shard, device):
+        self.shard = shard
+        w, r = shard.world, shard.rank
+        tl = lambda a: torch.as_tensor(np.asarray(a, dtype=np.int64), dtype=torch.long, device=device)
+        self.send_counts = [0 if j == r else len(halo["send"][j]) for j in range(w)]
+        self.recv_counts = [0 if j == r else len(halo["recv"][j]) for j in range(w)]
+        self.send_idx = tl(np.concatenate([halo["send"][j] for j in range(w) if j != r]) if w > 1 else [])
+        self.recv_idx = tl(np.concatenate([halo["recv"][j] for j in range(w) if j != r]) if w > 1 else [])
+        self.active = (sum(self.send_counts) + sum(self.recv_counts)) > 0
+
+    def _a2a(self, out, inp, out_splits, in_splits):
+        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.shard.group)
+
+    def forward_add(self, rows):
+        "rows (q, V): adds into owned shared rows the partial sums the other ranks computed for them (in rank order)"
+        V = rows.shape[1]
+        inp = rows.index_select(0, self.send_idx).contiguous()
+        out = torch.empty((int(self.recv_idx.numel()), V), dtype=rows.dtype, device=rows.device)
+        self._a2a(out, inp, [c for c in self.recv_counts], [c for c in self.send_counts])
+        # a row can be shared with more than one rank: accumulate peer by peer (deterministic order)
+        off = 0
+        for c in self.recv_counts:
+            if c:
+                rows.index_add_(0, self.recv_idx[off:off + c], out[off:off + c])
+                off += c
+        return rows
+
+    def backward_return(self, rows):
+        "rows (q, V): overwrites the rows owned elsewhere with the values their owners hold"
+        V = rows.shape[1]
+        inp = rows.index_select(0, self.recv_idx).contiguous()
+        out = torch.empty((int(self.send_idx.numel()), V), dtype=rows.dtype, device=rows.device)
+        self._a2a(out, inp, [c for c in self.send_counts], [c for c in self.recv_counts])
+        rows.index_copy_(0, self.send_idx, out)
+        return rows
+
+
+# --------------------------------------------------------------------------------------------------- sharded evaluator
+
+class ShardedEvaluator:
+    "ConstraintEvaluator over this rank's subdomains and points + the halo exchange with the other ranks"
+
+    def __init__(self, ev: ConstraintEvaluator, halo, shard):
+        self.ev, self.shard = ev, shard
+        dev = ev.x.device
+        self.halo = HaloExchange(halo, shard, dev)
+        self.owned_idx = torch.as_tensor(np.nonzero(halo["owned_local"])[0], dtype=torch.long, device=dev)
+        t = ev.takes
+        if not (t.q == t.n and t.npou == 1):
+            raise NotImplementedError("sharded evaluation needs one row per local point (npou == 1)")
+        self.nsum = torch.empty((max(t.q, 1), ev.V), dtype=torch.float32, device=dev)[:t.q]
+        # denominators: local partial -> total on the owners (once per active-set change)
+        self.halo.forward_add(ev.dsum[:t.q])          # collective: every rank calls it, even with no rows
+
+    def forward(self, params):
+        lib = _lib.load()
+        ev = self.ev
+        tv = ev.takes.view()
+        check(lib.fbp_forward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
+                              ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, stream_ptr()), "fbp_forward")
+        check(lib.fbp_row_sums(ev.plan.handle, C.byref(tv), ptr(ev.pair_out), ptr(self.nsum), stream_ptr()), "fbp_row_sums")
+        self.halo.forward_add(self.nsum)
+        ujets = torch.empty((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
+        check(lib.fbp_reduce_rows_forward(ev.plan.handle, C.byref(tv), ptr(self.nsum), ptr(ev.dsum), ptr(ujets),
+                                          stream_ptr()), "fbp_reduce_rows_forward")
+        return ujets.index_select(0, self.owned_idx)
+
+    def backward(self, ujets_bar_owned, params, grads):
+        lib = _lib.load()
+        ev = self.ev
+        tv = ev.takes.view()
+        ub = torch.zeros((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
+        ub.index_copy_(0, self.owned_idx, ujets_bar_owned.contiguous().float())
+        check(lib.fbp_reduce_backward(ev.plan.handle, C.byref(tv), ptr(ub), ptr(ev.dsum), ptr(ev.grow), stream_ptr()),
+              "fbp_reduce_backward")
+        self.halo.backward_return(ev.grow[:ev.takes.q])
+        check(lib.fbp_backward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
+                               ptr(ev.grow), ptr(grads), 1, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats,
+                               stream_ptr()), "fbp_backward")
+
+
+class _ShardedSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tape_hook, sev, params, grads, weight):
+        ctx.sev, ctx.params, ctx.grads, ctx.weight = sev, params, grads, weight
+        return sev.forward(params)
+
+    @staticmethod
+    def backward(ctx, ubar):
+        ctx.sev.backward(ubar * ctx.weight, ctx.params, ctx.grads)
+        return None, None, None, None, None
+
+
+def sharded_sum(sev, params, grads, tape_hook, weight):
+    return _ShardedSum.apply(tape_hook, sev, params, grads, weight)
+
+
+# --------------------------------------------------------------------------------------------------- update inputs / step
+
+def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, constraints_global, constraint_offsets,
+                              jets, layer_sizes, kernel="auto"):
+    """Sharded counterpart of trainers.get_update_inputs: the global active-set algebra is identical on every rank
+    (every rank holds the full point set and the full static decomposition — both small), then takes are built for
+    this rank's block of subdomains over the points inside them."""
+    from .trainers import UpdateInputs, active_set_algebra
+    m = dd.m
+    if dd.npou != 1:
+        raise NotImplementedError("sharding supports a single partition of unity (RectangularDecompositionND)")
+    active = np.array(active).copy()
+    dev = dd.device
+    ims1 = torch.as_tensor(np.arange(m, dtype=np.int32)[active == 1], dtype=torch.int32, device=dev)
+    pt_count, mc1 = dd.inside_count(x_batch_global, models=ims1)
+    training_ips = nonzero_i32(pt_count)
+    d_stat = float(mc1.double().mean().item() ** (1 / dd.xd)) if ims1.numel() else float("nan")
+    x_batch = gather_rows(x_batch_global, training_ips)
+    ips_host = training_ips.cpu().numpy().astype(np.int64)
+    sizes = [c_[0].shape[0] for c_ in constraints_global]
+    bounds = np.searchsorted(ips_host, np.concatenate([constraint_offsets, [constraint_offsets[-1] + sizes[-1]]]))
+    _, model_count = dd.inside_count(x_batch, models=None)
+    active2, active_ims, fixed_ims, all_ims, _ = active_set_algebra(active, model_count.cpu().numpy())
+
+    blocks = [shard.block(m, j) for j in range(shard.world)]
+    lo, hi = blocks[shard.rank]
+    a_loc = active_ims[(active_ims >= lo) & (active_ims < hi)]
+    f_loc = fixed_ims[(fixed_ims >= lo) & (fixed_ims < hi)]
+    all_loc = np.concatenate([a_loc, f_loc]).astype(np.int32)
+    pos_loc = -np.ones(m, dtype=np.int32)
+    pos_loc[all_loc] = np.arange(len(all_loc), dtype=np.int32)
+
+    out = UpdateInputs()
+    out.active, out.active_ims, out.fixed_ims, out.all_ims = active2, a_loc.astype(np.int32), f_loc.astype(np.int32), all_loc
+    out.global_active_ims, out.global_all_ims = active_ims, all_ims
+    out.pos_of_model, out.training_ips, out.d, out.x_batch = pos_loc, training_ips, d_stat, x_batch
+    out.constraints, out.takess, out.evaluators, out.weights, out.halos = [], [], [], [], []
+    sorted_all = np.sort(all_ims)
+    for ic in range(len(constraints_global)):
+        a, b = int(bounds[ic]), int(bounds[ic + 1])
+        local = (training_ips[a:b] - int(constraint_offsets[ic])).contiguous()
+        con = [gather_rows(c_, local) for c_ in constraints_global[ic]]
+        x_ic = con[0]
+        inside = []
+        for (l, h) in blocks:
+            ims_j = sorted_all[(sorted_all >= l) & (sorted_all < h)].astype(np.int32)
+            if len(ims_j) and x_ic.shape[0]:
+                ptj, _ = dd.inside_count(x_ic, models=torch.as_tensor(ims_j, dtype=torch.int32, device=dev),
+                                         want_model_count=False)
+                inside.append((ptj > 0).cpu().numpy())
+            else:
+                inside.append(np.zeros(x_ic.shape[0], dtype=bool))
+        halo = build_halo_lists(np.stack(inside), shard.rank)
+        lips = torch.as_tensor(halo["local_ips"].astype(np.int32), dtype=torch.int32, device=dev)
+        x_loc = gather_rows(x_ic, lips)
+        plan = Plan(layer_sizes, jets[ic], kernel=kernel)
+        takes = DeviceTakes(dd, x_loc, pos_loc, all_loc, len(a_loc), tile_points=plan.tile_points)
+        ev = ConstraintEvaluator(plan, takes, x_loc, dd)
+        sev = ShardedEvaluator(ev, halo, shard)
+        owned_global = torch.as_tensor(halo["local_ips"][halo["owned_local"]].astype(np.int32), dtype=torch.int32, device=dev)
+        out.constraints.append([gather_rows(c_, owned_global) for c_ in con])      # the loss sees owned points only
+        out.takess.append(takes)
+        out.evaluators.append(sev)
+        out.halos.append(halo)
+        n_ic = x_ic.shape[0]
+        out.weights.append(float(len(owned_global)) / float(max(n_ic, 1)))
+    return out
+
+
+def make_sharded_update(base_cls):
+    """UpdateStep variant whose forward goes through the sharded evaluators and which all-reduces the loss and the
+    problem-parameter gradients."""
+
+    class ShardedUpdateStep(base_cls):
+        def __init__(self, shard, *a, **kw):
+            super().__init__(*a, **kw)
+            self.shard = shard
+
+        def forward_loss(self):
+            self._refresh_problem_views()
+            cons = []
+            for sev, con, w in zip(self.inp.evaluators, self.inp.constraints, self.inp.weights):
+                ujets = sharded_sum(sev, self.params, self.grads, self.hook, w)
+                jet = sev.ev.plan.jet
+                if self.has_constraining:
+                    ujs = jet.ujs_constrained(ujets, con[0], self.problem.constraining_fn, self.all_params)
+                else:
+                    ujs = jet.ujs_plain(ujets)
+                cons.append(list(con) + ujs)
+            return self.problem.loss_fn(self.all_params, cons)
+
+        def _eager(self):
+            self.grads.zero_()
+            if self.prob_flat is not None:
+                self.prob_flat.grad = None
+            self.hook.grad = None
+            loss = self.forward_loss()
+            loss.backward()
+            w0 = self.inp.weights[0]
+            pg = None
+            if self.prob_flat is not None and self.prob_flat.numel():
+                pg = self.prob_flat.grad if self.prob_flat.grad is not None else torch.zeros_like(self.prob_flat)
+                pg = pg * w0
+                dist.all_reduce(pg, group=self.shard.group)
+            with torch.no_grad():
+                gl = (loss.detach() * w0).reshape(1)
+                dist.all_reduce(gl, group=self.shard.group)
+                self.adam.step(self.params, self.grads, self.active_ims_dev,
+                               self.prob_flat.data if pg is not None else None, pg)
+                self.loss_out.copy_(gl[0])
+            return self.loss_out
+
+    return ShardedUpdateStep

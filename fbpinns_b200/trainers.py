@@ -304,10 +304,20 @@ class FBPINNTrainer(_Trainer):
         c = self.c
         t0 = time.time()
         logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs..")
-        self.inputs = get_update_inputs(active, self.all_params, self.dd, self.x_batch_global, self.constraints_global,
-                                        self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel)
-        self.update = UpdateStep(self.inputs, self.params, self.adam, self.all_params, self.prob_flat, c.problem,
-                                 c.use_cuda_graph)
+        shard = getattr(self, "shard", None)
+        if shard is None or shard.world == 1:
+            self.inputs = get_update_inputs(active, self.all_params, self.dd, self.x_batch_global, self.constraints_global,
+                                            self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel)
+            self.update = UpdateStep(self.inputs, self.params, self.adam, self.all_params, self.prob_flat, c.problem,
+                                     c.use_cuda_graph)
+        else:
+            from . import parallel
+            self.inputs = parallel.get_update_inputs_sharded(shard, active, self.all_params, self.dd, self.x_batch_global,
+                                                             self.constraints_global, self.constraint_offsets, self.jets,
+                                                             self.layer_sizes, kernel=c.kernel)
+            self.update = parallel.make_sharded_update(UpdateStep)(shard, self.inputs, self.params, self.adam,
+                                                                   self.all_params, self.prob_flat, c.problem,
+                                                                   c.use_cuda_graph)
         self.n_rebuilds += 1
         torch.cuda.synchronize()
         logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs done ({time.time() - t0:.2f} s); "
@@ -318,11 +328,21 @@ class FBPINNTrainer(_Trainer):
         "One FBPINN_update on the current active set; returns the device scalar loss (no host sync)."
         return self.update()
 
+    def point_buffers(self):
+        "device tensors holding the collocation points a step reads (one or two per constraint)"
+        bufs = []
+        for ev, con in zip(self.inputs.evaluators, self.inputs.constraints):
+            x_kernel = ev.ev.x if hasattr(ev, "ev") else ev.x
+            bufs.append(x_kernel)
+            if con[0].data_ptr() != x_kernel.data_ptr():
+                bufs.append(con[0])
+        return bufs
+
     def step_from_host(self, x_host_pinned_list):
-        """End-to-end step: copies each constraint's collocation points from (pinned) host memory into the device
-        buffers the kernels read, runs one update and returns the loss as a python float (device->host read)."""
-        for con, xh in zip(self.inputs.constraints, x_host_pinned_list):
-            con[0].copy_(xh, non_blocking=True)
+        """End-to-end step: copies the collocation points from (pinned) host memory into the device buffers of
+        point_buffers(), runs one update and returns the loss as a python float (device->host read)."""
+        for buf, xh in zip(self.point_buffers(), x_host_pinned_list):
+            buf.copy_(xh, non_blocking=True)
         return float(self.update().item())
 
     def train(self):

@@ -167,6 +167,11 @@ int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x
  * point's rows, divided by npou.  d_ujets [n][C*ud] (points without any pair get 0). */
 int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out,
                        const float* d_dsum, float* d_ujets, void* stream);
+/* The same in two steps, for the multi-GPU halo exchange: row sums d_nsum [q][C*ud] of the LOCAL pairs,
+ * then — after the partial sums of rows shared with other ranks have been added — the quotient rule from row sums. */
+int fbp_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out, float* d_nsum, void* stream);
+int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_nsum, const float* d_dsum,
+                            float* d_ujets, void* stream);
 /* Transpose of the above: cotangent of ujets [n][C*ud] -> cotangent of row numerators d_grow [q][C*ud]. */
 int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_ujets_bar,
                         const float* d_dsum, float* d_grow, void* stream);

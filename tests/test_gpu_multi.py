@@ -1,0 +1,76 @@
+"""Multi-GPU parity (needs >= 2 GPUs, otherwise skipped): the subdomain-sharded step (NCCL halo exchange) must
+reproduce the single-GPU loss curve and parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, name, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    try:
+        from fbpinns_b200 import configs
+        from fbpinns_b200.trainers import FBPINNTrainer
+        from fbpinns_b200.parallel import shard_trainer
+        from fbpinns_b200.util.logger import logger
+        logger.setLevel("WARNING")
+        n_steps = 12
+
+        def make(graph):
+            if name == "cfg5":
+                return configs.cfg5_poisson(n_sub=(8, 6), n_pts=(96, 72), device=f"cuda:{rank}", use_cuda_graph=graph)
+            if name == "cfg2":
+                return configs.cfg2_harmonic_oscillator_inverse(n_sub=10, n_pts=120, device=f"cuda:{rank}", use_cuda_graph=graph)
+            return configs.cfg3_burgers(n_sub=(6, 5), n_pts=(48, 40), line_scheduler=False, device=f"cuda:{rank}",
+                                        use_cuda_graph=graph)
+        # single-GPU reference trajectory (every rank computes the same one)
+        ref = FBPINNTrainer(make(False)).setup()
+        ref.set_active(np.ones(ref.dd.m, dtype=int))
+        ref_losses = [float(ref.step().item()) for _ in range(n_steps)]
+        out = {}
+        for graph in (False, True):
+            tr = shard_trainer(FBPINNTrainer(make(graph)), rank, world).setup()
+            tr.set_active(np.ones(tr.dd.m, dtype=int))
+            losses = [float(tr.step().item()) for _ in range(n_steps)]
+            lo, hi = tr.shard.block(tr.dd.m)
+            perr = float((tr.params[lo:hi] - ref.params[lo:hi]).abs().max() / ref.params.abs().max())
+            pe = 0.0
+            if tr.prob_flat is not None:
+                pe = float((tr.prob_flat - ref.prob_flat).abs().max())
+            out[graph] = (losses, perr, pe, tr.update.graph is not None)
+        q.put((rank, ref_losses, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["cfg5", "cfg3", "cfg2"])
+def test_sharded_step_matches_single_gpu(name):
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if world < 4 else 4
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, ref_losses, out in res:
+        for graph, (losses, perr, pe, captured) in out.items():
+            rel = np.max(np.abs(np.array(losses) - np.array(ref_losses)) / np.abs(np.array(ref_losses)))
+            assert rel < 1e-4, (name, rank, graph, rel, losses, ref_losses)
+            assert perr < 1e-4, (name, rank, graph, perr)
+            assert pe < 1e-4, (name, rank, graph, pe)
+            if graph:
+                assert captured

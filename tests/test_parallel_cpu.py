@@ -1,0 +1,95 @@
+"""CPU tests of the multi-GPU host logic with the gloo backend, world_size 2 (no GPU): ownership, halo lists and
+the row exchange must reproduce the single-process row sums, and return owners' cotangents to the sharers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ref_takes
+from fbpinns_b200 import configs
+from fbpinns_b200.parallel import Shard, build_halo_lists, HaloExchange
+
+
+def _geometry(world):
+    c = configs.cfg3_burgers(n_sub=(6, 4), n_pts=(40, 30))
+    decomp = ref_takes.rectangular_init_params(**c.decomposition_init_kwargs)
+    m = decomp["m"]
+    xs = [np.linspace(-1, 1, 40), np.linspace(0, 1, 30)]
+    x = np.stack(np.meshgrid(*xs, indexing="ij"), -1).reshape(-1, 2).astype(np.float32)
+    mask = ref_takes.inside_mask(decomp, x, np.arange(m))               # (n, m)
+    blocks = [Shard(j, world).block(m) for j in range(world)]
+    inside = np.stack([mask[:, lo:hi].any(1) for lo, hi in blocks])   # (world, n)
+    return x, mask, blocks, inside
+
+
+def test_halo_lists_are_consistent():
+    for world in (2, 3, 4):
+        x, mask, blocks, inside = _geometry(world)
+        halos = [build_halo_lists(inside, r) for r in range(world)]
+        owner = halos[0]["owner"]
+        assert (owner >= 0).all()
+        # every point is owned exactly once, by the lowest rank that contains it
+        owned = np.zeros(len(x), int)
+        for r, h in enumerate(halos):
+            owned[h["local_ips"][h["owned_local"]]] += 1
+            assert (inside[:r, h["local_ips"][h["owned_local"]]] == False).all()
+        assert (owned == 1).all()
+        # send list of r towards j == recv list of j from r, as global point indices in the same order
+        for r in range(world):
+            for j in range(world):
+                if j == r:
+                    continue
+                a = halos[r]["local_ips"][halos[r]["send"][j]]
+                b = halos[j]["local_ips"][halos[j]["recv"][r]]
+                assert np.array_equal(a, b)
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x, mask, blocks, inside = _geometry(world)
+        shard = Shard(rank, world)
+        halo = build_halo_lists(inside, rank)
+        ex = HaloExchange(halo, shard, torch.device("cpu"))
+        lo, hi = blocks[rank]
+        lips = halo["local_ips"]
+        # per-pair value f(point, model); local partial row sums over this rank's models
+        pv = (np.arange(mask.shape[0])[:, None] * 0.001 + np.arange(mask.shape[1])[None, :] * 1.0 + 0.5)
+        local = (mask[:, lo:hi] * pv[:, lo:hi]).sum(1)[lips]
+        total = (mask * pv).sum(1)[lips]
+        rows = torch.tensor(np.stack([local, 2 * local], 1), dtype=torch.float64)
+        ex.forward_add(rows)
+        own = halo["owned_local"]
+        ok_fwd = np.allclose(rows.numpy()[own, 0], total[own]) and np.allclose(rows.numpy()[own, 1], 2 * total[own])
+        # reverse: owners hold g(point); sharers must receive it
+        g = np.sin(lips * 0.37)
+        back = torch.tensor(np.where(own, g, 0.0)[:, None].repeat(3, 1), dtype=torch.float64)
+        ex.backward_return(back)
+        ok_bwd = np.allclose(back.numpy()[:, 0], g)
+        q.put((rank, bool(ok_fwd), bool(ok_bwd), int(own.sum()), int(len(lips))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_halo_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    x, mask, blocks, inside = _geometry(world)
+    assert sum(r[3] for r in res) == len(x)                  # every point owned once
+    for rank, ok_fwd, ok_bwd, n_own, n_loc in res:
+        assert ok_fwd and ok_bwd, (rank, ok_fwd, ok_bwd)
+        assert n_loc > n_own or rank == 0
