@@ -1,0 +1,143 @@
+"""Golden vectors made by running the REFERENCE'S OWN SOURCE under a numpy shim (tests/golden/make_golden_shim.py):
+pins the oracle (CPU) and, through the same fixtures, the CUDA path (GPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_takes, ref_model
+from fbpinns_b200 import problems, decompositions
+from fbpinns_b200.jets import JetSpec, get_jmaps
+import common
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from cases import NAMES, case_setup  # noqa: E402
+
+
+def _load(name):
+    g = np.load(os.path.join(HERE, "golden", f"refmodel_{name}.npz"), allow_pickle=True)
+    cs = case_setup(name)
+    assert np.array_equal(g["x"], cs["x"]) and repr(cs["req"]) == str(g["req_repr"])
+    nl = len(cs["layer_sizes"]) - 1
+    layers = [(g[f"W{l}"], g[f"b{l}"]) for l in range(nl)]
+    return g, cs, layers
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_decomposition_and_jmaps_match_reference(name):
+    g, cs, _ = _load(name)
+    xd = len(cs["dkw"]["subdomain_xs"])
+    ours = decompositions.RectangularDecompositionND._get_level_params(0, xd, **cs["dkw"])
+    orac = ref_takes.level_params(0, xd, cs["dkw"]["subdomain_xs"], cs["dkw"]["subdomain_ws"], cs["dkw"]["unnorm"])
+    for i in range(7):
+        assert np.array_equal(np.asarray(ours[i]), g[f"level_{i}"]), i      # float64, bit for bit
+        assert np.array_equal(np.asarray(orac[i]), g[f"level_{i}"]), i
+    sd, _ = decompositions.RectangularDecompositionND.init_params(**cs["dkw"])
+    od = ref_takes.rectangular_init_params(**cs["dkw"])
+    for i in range(6):
+        assert np.array_equal(sd["subdomain"]["params"][i].numpy(), g[f"static_{i}"])
+        assert np.array_equal(od["subdomain"]["params"][i], g[f"static_{i}"])
+    assert np.array_equal(sd["xmins0"], g["xmins0"]) and np.array_equal(sd["xmaxs0"], g["xmaxs0"])
+    assert repr(get_jmaps(cs["req"])) == str(g["jmaps_repr"])
+    assert repr(ref_model.get_jmaps(cs["req"])) == str(g["jmaps_repr"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_get_inputs_matches_reference(name):
+    g, cs, _ = _load(name)
+    decomp = ref_takes.rectangular_init_params(**cs["dkw"])
+    takes, all_ims, a_ims, f_ims, active = ref_takes.get_inputs(cs["x"], g["active_in"], decomp)
+    assert np.array_equal(active, g["active_out"]) and np.array_equal(all_ims, g["all_ims"])
+    for got, nm in zip(takes[:4], ["m_take", "n_take", "p_take", "np_take"]):
+        assert np.array_equal(got, g[nm]), nm
+    assert takes[4] == int(g["npou"])
+    # host-side algebra of the product
+    from fbpinns_b200.trainers import active_set_algebra
+    counts = ref_takes.inside_mask(decomp, cs["x"], np.arange(decomp["m"])).sum(0)
+    act2, a2, f2, all2, pos = active_set_algebra(g["active_in"], counts)
+    assert np.array_equal(act2, g["active_out"]) and np.array_equal(all2, g["all_ims"])
+
+
+def _oracle_model(g, cs, layers, dtype=torch.float64, constrained=True):
+    decomp = ref_takes.rectangular_init_params(**cs["dkw"])
+    all_ims = g["all_ims"]
+    dc = ref_model.cut_decomp(ref_model.to_torch(decomp, dtype), all_ims)
+    lc = [(torch.as_tensor(w[all_ims], dtype=dtype), torch.as_tensor(b[all_ims], dtype=dtype)) for w, b in layers]
+    takes = (g["m_take"], g["n_take"], g["p_take"], g["np_take"], int(g["npou"]))
+    prob = getattr(problems, cs["problem"])
+    sp, _ = prob.init_params(**cs["pkw"])
+    ap = {"static": {"problem": {k: (v.to(dtype) if torch.is_tensor(v) else v) for k, v in sp.items()}}, "trainable": {}}
+    x = torch.as_tensor(cs["x"], dtype=dtype)
+    cf = prob.constraining_fn if constrained else None
+    return dc, lc, takes, prob, ap, x, cf
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_model_values_match_reference(name):
+    "FBPINN_model of the reference (its own norm/network/unnorm/window/segment-sum/constraining code) vs the oracle"
+    g, cs, layers = _load(name)
+    dc, lc, takes, prob, ap, x, cf = _oracle_model(g, cs, layers)
+    u, wp, us, ws, us_raw = ref_model.fbpinn_model(dc, lc, x, takes, cf, ap)
+    for got, nm in [(u, "u"), (wp, "wp"), (us, "us"), (ws, "ws"), (us_raw, "us_raw")]:
+        assert np.allclose(got.numpy(), g[nm], rtol=1e-12, atol=1e-13), nm
+    u0 = ref_model.fbpinn_model(dc, lc, x, takes, None, ap)[0]
+    assert np.allclose(u0.numpy(), g["u_unconstrained"], rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_ujs_match_finite_differences_of_reference(name):
+    "nested-jvp ujs of the oracle vs central finite differences of the reference's own FBPINN_model (float64)"
+    g, cs, layers = _load(name)
+    dc, lc, takes, prob, ap, x, cf = _oracle_model(g, cs, layers)
+    ujs = ref_model.fbpinn_forward(dc, lc, x, takes, ref_model.get_jmaps(cs["req"]), cf, ap)
+    for j, uj in enumerate(ujs):
+        e = common.rel_err(uj.numpy(), g[f"uj_fd_{j}"])
+        assert e < 2e-6, (name, j, e)
+    # the torch restatement of loss_fn against the reference's loss_fn on the same ujs
+    cons = [[x] + [torch.as_tensor(g[f"uj_fd_{j}"]) for j in range(len(cs["req"]))]]
+    ours = float(prob.loss_fn(ap, cons))
+    assert abs(ours - float(g["loss_on_fd_ujs"])) <= 1e-10 * abs(float(g["loss_on_fd_ujs"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("kernel", ["generic", "auto"])
+def test_cuda_path_matches_reference_golden(name, kernel):
+    "CUDA kernels through the C ABI on the golden inputs: takes bit-exact, u and ujs within 1e-5"
+    from fbpinns_b200.engine import DeviceDecomposition, DeviceTakes, ConstraintEvaluator, Plan, pack_params
+    from fbpinns_b200.trainers import active_set_algebra
+    g, cs, layers = _load(name)
+    dev = torch.device("cuda:0")
+    sd, _ = decompositions.RectangularDecompositionND.init_params(**cs["dkw"])
+    dd = DeviceDecomposition(sd["subdomain"]["params"], sd["subdomain"]["pou"], dev)
+    x = torch.as_tensor(cs["x"], device=dev)
+    _, mc = dd.inside_count(x)
+    act2, a_ims, f_ims, all_ims, pos = active_set_algebra(g["active_in"], mc.cpu().numpy())
+    assert np.array_equal(all_ims, g["all_ims"])
+    xd, ud = x.shape[1], 1
+    jet = JetSpec(cs["req"], xd, ud)
+    plan = Plan(cs["layer_sizes"], jet, kernel=kernel)
+    takes = DeviceTakes(dd, x, pos, all_ims, len(a_ims), tile_points=plan.tile_points)
+    for got, nm in zip(takes.reference_arrays()[:4], ["m_take", "n_take", "p_take", "np_take"]):
+        assert np.array_equal(got, g[nm]), nm
+    params = pack_params(plan, [(torch.as_tensor(w, device=dev), torch.as_tensor(b, device=dev)) for w, b in layers])
+    ev = ConstraintEvaluator(plan, takes, x, dd)
+    ujets = ev.forward(params)
+    prob = getattr(problems, cs["problem"])
+    sp, _ = prob.init_params(**cs["pkw"])
+    ap = {"static": {"problem": {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sp.items()}}, "trainable": {}}
+    ujs = jet.ujs_constrained(ujets, x, prob.constraining_fn, ap)
+    for j, uj in enumerate(ujs):
+        e = common.rel_err(uj.cpu().numpy(), g[f"uj_fd_{j}"])
+        assert e < 1e-5, (name, kernel, j, e)
+    # value path (what FBPINN_model_jit returns): u and the window sums wp
+    vplan = Plan(cs["layer_sizes"], JetSpec(((0, ()),), xd, ud), kernel=kernel)
+    vev = ConstraintEvaluator(vplan, takes, x, dd)
+    u = prob.constraining_fn(ap, x, vev.forward(params))
+    assert common.rel_err(u.cpu().numpy(), g["u"]) < 1e-5
+    assert common.rel_err(vev.dsum[:takes.q, 0].cpu().numpy(), g["wp"][:, 0]) < 1e-5
+    us = vev.pair_values_reference_order()[:, 0].cpu().numpy()
+    assert common.rel_err(us, g["us"][:, 0]) < 1e-5
