@@ -337,7 +337,14 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL kernels must go before the communicator; destroy_process_group() can hang
+        # on them, so: drop the graphs, synchronise, barrier, and leave without the NCCL teardown.
+        tr.update.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -4,7 +4,7 @@
 set -x
 TAG=${1:-r1}
 # every launch of a short bench with its device time (cold-cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --skip-cpu --no-graph > gpurun_out/launches_$TAG.log 2>&1
 # full capture of the two tiled kernels (one forward + one backward launch)
 ncu --set full --clock-control none --import-source on -k regex:fast_.*_kernel -s 6 -c 3 -f -o gpurun_out/prof_$TAG \

@@ -84,9 +84,25 @@ def test_halo_exchange_gloo(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(world)]
+    import queue as _queue
+    import time as _time
+    res, t_end = [], _time.time() + 420
+    while len(res) < world and _time.time() < t_end:
+        try:
+            res.append(q.get(timeout=2))
+        except _queue.Empty:
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead:                                   # a worker crashed: do not wait for the others
+                for p in procs:
+                    if p.is_alive():
+                        p.terminate()
+                raise AssertionError(f"worker exited with code {dead[0].exitcode}")
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():
+            p.terminate()
+    assert len(res) == world, "workers did not finish in time"
+    for p in procs:
         assert p.exitcode == 0
     x, mask, blocks, inside = _geometry(world)
     assert sum(r[3] for r in res) == len(x)                  # every point owned once
