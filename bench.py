@@ -262,13 +262,14 @@ def run_ours(args):
 
     def k_fwd():
         check(lib.fbp_forward(ev.plan.handle, Cc.byref(tv), ptr(ev.x), ptr(tr.params), ptr(tr.dd.sub_static),
-                              ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, stream_ptr()), "fbp_forward")
+                              ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, ptr(ev.cache), stream_ptr()), "fbp_forward")
 
     check(lib.fbp_reduce_backward(ev.plan.handle, Cc.byref(tv), ptr(ubar), ptr(ev.dsum), ptr(ev.grow), stream_ptr()), "rb")
 
     def k_bwd():
         check(lib.fbp_backward(ev.plan.handle, Cc.byref(tv), ptr(ev.x), ptr(tr.params), ptr(tr.dd.sub_static), ptr(ev.grow),
-                               ptr(grads), 0, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats, stream_ptr()), "fbp_backward")
+                               ptr(grads), 0, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats, ptr(ev.cache), stream_ptr()),
+              "fbp_backward")
 
     reps = max(5, min(args.steps, 20))
     k_fwd(); k_bwd()

@@ -55,6 +55,7 @@ SIGNATURES = {
     "fbp_plan_tile_points": (_I32, [_P]),
     "fbp_plan_set_kernel": (C.c_int, [_P, _I32]),
     "fbp_plan_scratch_per_pair": (_I64, [_P]),
+    "fbp_plan_cache_per_pair": (_I64, [_P]),
     "fbp_pack_params": (C.c_int, [_P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _P]),
     "fbp_unpack_params": (C.c_int, [_P, _I64, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "fbp_inside_count": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P]),
@@ -65,13 +66,13 @@ SIGNATURES = {
     "fbp_takes_emit": (C.c_int, [_P] + [_P] * 11 + [_P]),
     "fbp_takes_destroy": (C.c_int, [_P]),
     "fbp_window_sums": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
-    "fbp_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I64, _P]),
+    "fbp_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I64, _P, _P]),
     "fbp_reduce_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
     "fbp_reduce_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
     "fbp_row_sums": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P]),
     "fbp_reduce_rows_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
     "fbp_backward_workspace_floats": (_I64, [_P, C.POINTER(TakesView)]),
-    "fbp_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I32, _P, _P, _I64, _P]),
+    "fbp_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _P]),
     "fbp_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I32, _F, _F, _F, _F, _F, _P]),
     "fbp_fma_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
 }

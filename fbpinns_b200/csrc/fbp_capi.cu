@@ -117,6 +117,11 @@ int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
     return 0;
 }
 
+int64_t fbp_plan_cache_per_pair(const fbp_plan* plan) {
+    if (!plan) return -1;
+    return (plan->use_fast() && plan->fast.nhid == 2) ? (int64_t)plan->fast.H * plan->dev.C : 0;
+}
+
 int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan) {
     if (!plan) return -1;
     return plan->use_fast() ? 0 : (int64_t)plan->dev.hid_total * plan->dev.C;
@@ -130,10 +135,12 @@ static int check_view(const fbp_takes_view* tv, const char* who) {
 }
 
 int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
-                const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats, void* stream) {
+                const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats, float* d_act_cache,
+                void* stream) {
     FBP_REQUIRE(plan, "fbp_forward: null plan");
     if (int rc = check_view(tv, "fbp_forward")) return rc;
-    if (plan->use_fast()) return fbp_fast_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, (cudaStream_t)stream);
+    if (plan->use_fast())
+        return fbp_fast_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, d_act_cache, (cudaStream_t)stream);
     return fbp_generic_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, d_scratch, scratch_floats, (cudaStream_t)stream);
 }
 
@@ -144,11 +151,12 @@ int64_t fbp_backward_workspace_floats(const fbp_plan* plan, const fbp_takes_view
 
 int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                  const float* d_sub_static, const float* d_grow, float* d_grads, int32_t accumulate, float* d_gpart,
-                 float* d_scratch, int64_t scratch_floats, void* stream) {
+                 float* d_scratch, int64_t scratch_floats, const float* d_act_cache, void* stream) {
     FBP_REQUIRE(plan, "fbp_backward: null plan");
     if (int rc = check_view(tv, "fbp_backward")) return rc;
     if (plan->use_fast())
-        return fbp_fast_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_gpart, (cudaStream_t)stream);
+        return fbp_fast_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_gpart, d_act_cache,
+                                 (cudaStream_t)stream);
     return fbp_generic_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_scratch,
                                 scratch_floats, (cudaStream_t)stream);
 }

@@ -157,8 +157,8 @@ int fbp_generic_backward(const fbp_plan* plan, const fbp_takes_view* tv, const f
 // tiled family: returns -1 if no instance matches
 int fbp_fast_lookup(const fbp_plan_desc* desc, FastSpec* spec);
 int fbp_fast_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
-                     const float* d_sub_static, float* d_pair_out, cudaStream_t stream);
+                     const float* d_sub_static, float* d_pair_out, float* d_cache, cudaStream_t stream);
 int64_t fbp_fast_backward_workspace(const fbp_plan* plan, const fbp_takes_view* tv);
 int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                       const float* d_sub_static, const float* d_grow, float* d_grads, int accumulate, float* d_gpart,
-                      cudaStream_t stream);
+                      const float* d_cache, cudaStream_t stream);

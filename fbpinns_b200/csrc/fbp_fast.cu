@@ -59,7 +59,7 @@ static void fill_args(const fbp_plan* plan, const fbp_takes_view* tv, const floa
                       const float* d_sub_static, FastArgs& a) {
     a.x = d_x; a.params = d_params; a.sub_static = d_sub_static;
     a.sub_ids = tv->d_sub_ids; a.spair_point = tv->d_spair_point; a.spair_row = tv->d_spair_row; a.items = tv->d_items;
-    a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr;
+    a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr; a.cache = nullptr;
     a.xd = plan->dev.xd; a.P = plan->dev.P;
     for (int i = 0; i < FBP_MAX_XD; ++i) a.axis[i] = plan->fast.axis[i];
     for (int i = 0; i < FBP_MAX_COMP; ++i) a.ext[i] = plan->fast.ext[i];
@@ -77,12 +77,13 @@ static int dispatch(const fbp_plan* plan, bool backward, const FastArgs& a, int 
 }
 
 int fbp_fast_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
-                     const float* d_sub_static, float* d_pair_out, cudaStream_t stream) {
+                     const float* d_sub_static, float* d_pair_out, float* d_cache, cudaStream_t stream) {
     if (tv->n_items == 0) return 0;
     FBP_REQUIRE(tv->d_items != nullptr, "fbp_forward(tiled): takes view has no work list");
     FastArgs a;
     fill_args(plan, tv, d_x, d_params, d_sub_static, a);
     a.pair_out = d_pair_out;
+    a.cache = d_cache;
     return dispatch(plan, false, a, tv->n_items, stream);
 }
 
@@ -92,7 +93,7 @@ int64_t fbp_fast_backward_workspace(const fbp_plan* plan, const fbp_takes_view* 
 
 int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                       const float* d_sub_static, const float* d_grow, float* d_grads, int accumulate, float* d_gpart,
-                      cudaStream_t stream) {
+                      const float* d_cache, cudaStream_t stream) {
     if (tv->m_active == 0) return 0;
     FBP_REQUIRE(d_gpart != nullptr || tv->n_items_active == 0, "fbp_backward(tiled): null workspace");
     if (tv->n_items_active > 0) {
@@ -100,6 +101,7 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
         fill_args(plan, tv, d_x, d_params, d_sub_static, a);
         a.grow = d_grow;
         a.gpart = d_gpart;
+        a.cache = const_cast<float*>(d_cache);
         if (int rc = dispatch(plan, true, a, tv->n_items_active, stream)) return rc;
     }
     const int64_t total = (int64_t)tv->m_active * plan->dev.P;

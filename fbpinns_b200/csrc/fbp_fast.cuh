@@ -35,6 +35,8 @@ struct FastArgs {
     float* pair_out;     // forward output  [s][C]
     const float* grow;   // reverse input   [q][C]
     float* gpart;        // reverse output  [n_items_active][P]
+    float* cache;        // optional [s][H*C]: jets of the last hidden layer, written by the forward kernel per reverse
+                         // tile as [H][C][cnt] at float offset (first pair of the tile)*H*C, read back by the reverse
     int xd, P;
     int axis[FBP_MAX_XD];   // slot -> axis (NA2 slots first)
     int ext[FBP_MAX_COMP];  // internal component -> external component index
@@ -79,6 +81,35 @@ struct FastCfg {
     static constexpr int TPB = bwd_ok(128) ? 128 : (bwd_ok(64) ? 64 : 32);
     static constexpr int NTB = JG * (TPB / PPT);
 };
+
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a): global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// generic-proxy accesses to shared memory before this fence are ordered before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
 
@@ -307,6 +338,32 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
                     fast_tanh_jets<CF>(acc[j][p]);
                 }
             }
+            if (a.cache != nullptr) {
+                // save the hidden jets for the reverse kernel in ITS tile layout: [H][C][cntb] at (first+t0b)*H*C
+                constexpr int TPB = CF::TPB;
+                const int off = t0 + p0;                         // pair offset inside the work item (even)
+                if (off < count) {
+                    const int t0b = (off / TPB) * TPB;
+                    const int cntb = min(TPB, count - t0b);
+                    float* cb = a.cache + (int64_t)(first + t0b) * (H * C) + (off - t0b);
+                    const bool two = (off + 1 < count);
+                    if (cntb == TPB) {                           // full reverse tile: rows are 8-byte aligned
+#pragma unroll
+                        for (int j = 0; j < TM; ++j)
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                *reinterpret_cast<float2*>(cb + ((j0 + j) * C + c) * TPB) = make_float2(acc[j][0][c], acc[j][1][c]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TM; ++j)
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                cb[((j0 + j) * C + c) * cntb] = acc[j][0][c];
+                                if (two) cb[((j0 + j) * C + c) * cntb + 1] = acc[j][1][c];
+                            }
+                    }
+                }
+            }
         }
         // output layer (ud = 1): partial dot over this thread's TM units, reduced over the JG groups below
 #pragma unroll
@@ -358,7 +415,7 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
 // =====================================================================================================
 // reverse
 // =====================================================================================================
-template <class CF>
+template <class CF, bool USE_CACHE>
 __global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
     constexpr int H = CF::H, C = CF::C, TM = CF::TM, PPT = CF::PPT, JG = CF::JG, TP = CF::TPB, NT = CF::NTB;
     constexpr int NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
@@ -382,6 +439,9 @@ __global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
     float* rb = zs + 3 * TP;                         // [C][TP]   cotangent of the output-layer jets
     float* act0 = rb + C * TP;                       // [H][RS]
     float* act1 = act0 + H * RS;                     // [H][RS]   (NHID == 2)
+    __shared__ __align__(8) uint64_t cache_bar;      // mbarrier of the TMA loads into act1
+    constexpr bool CACHED = USE_CACHE && CF::NHID == 2;
+    constexpr uint32_t ROW_BYTES = C * TP * sizeof(float);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int item = blockIdx.x;
@@ -401,7 +461,22 @@ __global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
     const float flag = ss[2 * xd], un_sd = ss[2 * xd + 2];
     fast_load_params<CF, NT>(sm, a.params + (int64_t)im * a.P, xd, isd, a.axis, true);
     for (int i = tid; i < CF::SM_GRAD; i += NT) gs[i] = 0.0f;
+    if (CACHED && tid == 0) {
+        mbar_init(&cache_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    uint32_t cache_phase = 0;
+    // TMA prefetch of a FULL tile's saved hidden jets into act1: H bulk copies of one [C][TP] row block each
+    auto prefetch_tile = [&](int t0n) {
+        if (CACHED && tid == 0 && t0n < count && count - t0n >= TP) {
+            fence_proxy_async();
+            mbar_expect_tx(&cache_bar, (uint32_t)H * ROW_BYTES);
+            const float* src = a.cache + (int64_t)(first + t0n) * (H * C);
+            for (int k = 0; k < H; ++k) tma_bulk_g2s(act1 + k * RS, src + k * (C * TP), ROW_BYTES, &cache_bar);
+        }
+    };
+    prefetch_tile(0);
 
     const int jg = tid / (TP / PPT), pp = tid % (TP / PPT);
     const int j0 = jg * TM, p0 = pp * PPT;
@@ -461,7 +536,7 @@ __global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
         float acc[TM][PPT][C];
         fast_layer0<CF, TP>(sm, zs, j0, p0, acc);
         fast_store_act<CF, TP, RS>(act0, j0, p0, acc);
-        if (CF::NHID == 2) {
+        if (CF::NHID == 2 && !CACHED) {
             __syncthreads();
             fast_gemm<CF, TP, RS>(sm + CF::SM_WT1, act0, j0, p0, acc);
 #pragma unroll
@@ -474,6 +549,19 @@ __global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
                 }
             }
             fast_store_act<CF, TP, RS>(act1, j0, p0, acc);
+        }
+        if (CACHED) {
+            if (cnt == TP) {                               // full tile: wait for the TMA bytes (issued one tile ahead)
+                mbar_wait(&cache_bar, cache_phase);
+                cache_phase ^= 1;
+            } else {                                       // partial tile: plain loads of [H][C][cnt], zero padding
+                const float* src = a.cache + (int64_t)(first + t0) * (H * C);
+                for (int i = tid; i < H * C * TP; i += NT) {
+                    const int row = i / TP, p = i - row * TP;          // row = k*C + c
+                    const int k = row / C, c = row - k * C;
+                    act1[k * RS + c * TP + p] = p < cnt ? src[(int64_t)row * cnt + p] : 0.0f;
+                }
+            }
         }
         __syncthreads();
 
@@ -547,7 +635,8 @@ __global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
             }
             // ---- D: hbar0[k][(c,p)] = sum_j W1[j][k] abar1[j][(c,p)]  (raw matrix is "j-major" = k contiguous)
             fast_gemm<CF, TP, RS>(sm + CF::SM_WR1, act1, j0, p0, acc);
-            __syncthreads();      // every read of act0 by the G phase is done
+            __syncthreads();      // every read of act0 (G) and of act1 (G, D) is done
+            prefetch_tile(t0 + TP);
             // ---- tanh transpose of layer 0, in place: act0 <- abar0
 #pragma unroll
             for (int j = 0; j < TM; ++j) {
@@ -677,10 +766,12 @@ int fast_launch_one(bool backward, const FastArgs& a, int grid, cudaStream_t st)
         constexpr size_t bytes = sizeof(float) * CF::bwd_floats(TP);
         static bool configured = false;
         if (!configured) {
-            FBP_CHECK_CUDA(cudaFuncSetAttribute(fast_backward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            FBP_CHECK_CUDA(cudaFuncSetAttribute(fast_backward_kernel<CF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            FBP_CHECK_CUDA(cudaFuncSetAttribute(fast_backward_kernel<CF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             configured = true;
         }
-        fast_backward_kernel<CF><<<grid, CF::NTB, bytes, st>>>(a);
+        if (a.cache != nullptr && CF::NHID == 2) fast_backward_kernel<CF, true><<<grid, CF::NTB, bytes, st>>>(a);
+        else fast_backward_kernel<CF, false><<<grid, CF::NTB, bytes, st>>>(a);
     }
     FBP_LAUNCH_CHECK();
     return 0;

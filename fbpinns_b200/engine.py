@@ -62,6 +62,7 @@ class Plan:
         self.is_fast = bool(lib.fbp_plan_is_fast(self._h)) and mode != 1
         self.tile_points = int(lib.fbp_plan_tile_points(self._h))
         self.scratch_per_pair = int(lib.fbp_plan_scratch_per_pair(self._h))
+        self.cache_per_pair = int(lib.fbp_plan_cache_per_pair(self._h))
 
     @property
     def handle(self):
@@ -255,7 +256,7 @@ class ConstraintEvaluator:
 
     GENERIC_SCRATCH_FLOATS = 64 * 1024 * 1024   # 256 MB cap for the generic family's per-pair scratch
 
-    def __init__(self, plan: Plan, takes: DeviceTakes, x, decomp: DeviceDecomposition):
+    def __init__(self, plan: Plan, takes: DeviceTakes, x, decomp: DeviceDecomposition, activation_cache=True):
         lib = _lib.load()
         self.plan, self.takes, self.decomp = plan, takes, decomp
         self.x = x.contiguous()
@@ -276,6 +277,10 @@ class ConstraintEvaluator:
         ns = min(max(takes.s, 128) * spp, max(self.GENERIC_SCRATCH_FLOATS, 128 * spp)) if spp else 0
         self.scratch = f(max(ns, 1))
         self.scratch_floats = ns
+        # optional activation cache (tiled plans with two hidden layers): the forward kernel saves the last hidden
+        # layer's jets, the reverse kernel TMA-loads them instead of recomputing the hidden GEMM
+        ncache = takes.s * plan.cache_per_pair if activation_cache else 0
+        self.cache = torch.zeros(ncache, dtype=torch.float32, device=dev) if ncache else None
         check(lib.fbp_window_sums(plan.handle, C.byref(takes.view()), ptr(self.x), ptr(decomp.sub_static),
                                   ptr(self.dsum), stream_ptr()), "fbp_window_sums")
 
@@ -284,7 +289,8 @@ class ConstraintEvaluator:
         lib = _lib.load()
         tv = self.takes.view()
         check(lib.fbp_forward(self.plan.handle, C.byref(tv), ptr(self.x), ptr(params), ptr(self.decomp.sub_static),
-                              ptr(self.pair_out), ptr(self.scratch), self.scratch_floats, stream_ptr()), "fbp_forward")
+                              ptr(self.pair_out), ptr(self.scratch), self.scratch_floats, ptr(self.cache), stream_ptr()),
+              "fbp_forward")
         ujets = torch.empty((self.takes.n, self.V), dtype=torch.float32, device=self.x.device)
         check(lib.fbp_reduce_forward(self.plan.handle, C.byref(tv), ptr(self.pair_out), ptr(self.dsum), ptr(ujets),
                                      stream_ptr()), "fbp_reduce_forward")
@@ -299,7 +305,7 @@ class ConstraintEvaluator:
                                       stream_ptr()), "fbp_reduce_backward")
         check(lib.fbp_backward(self.plan.handle, C.byref(tv), ptr(self.x), ptr(params), ptr(self.decomp.sub_static),
                                ptr(self.grow), ptr(grads), 1 if accumulate else 0, ptr(self.gpart), ptr(self.scratch),
-                               self.scratch_floats, stream_ptr()), "fbp_backward")
+                               self.scratch_floats, ptr(self.cache), stream_ptr()), "fbp_backward")
 
     def pair_values_reference_order(self):
         """Per-pair numerator jets in the reference's (point-sorted) pair order, after a forward()."""

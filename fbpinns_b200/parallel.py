@@ -132,7 +132,7 @@ class ShardedEvaluator:
         ev = self.ev
         tv = ev.takes.view()
         check(lib.fbp_forward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
-                              ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, stream_ptr()), "fbp_forward")
+                              ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, ptr(ev.cache), stream_ptr()), "fbp_forward")
         check(lib.fbp_row_sums(ev.plan.handle, C.byref(tv), ptr(ev.pair_out), ptr(self.nsum), stream_ptr()), "fbp_row_sums")
         self.halo.forward_add(self.nsum)
         ujets = torch.empty((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
@@ -151,7 +151,7 @@ class ShardedEvaluator:
         self.halo.backward_return(ev.grow[:ev.takes.q])
         check(lib.fbp_backward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
                                ptr(ev.grow), ptr(grads), 1, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats,
-                               stream_ptr()), "fbp_backward")
+                               ptr(ev.cache), stream_ptr()), "fbp_backward")
 
 
 class _ShardedSum(torch.autograd.Function):

@@ -408,7 +408,7 @@ class FBPINNTrainer(_Trainer):
             _, mc = dd.inside_count(x)
             _, a_ims, f_ims, all_ims, pos = active_set_algebra(np.ones(dd.m, dtype=int), mc.cpu().numpy())
             takes = DeviceTakes(dd, x, pos, all_ims, len(a_ims), tile_points=plan.tile_points)
-            self._test_eval = (key, ConstraintEvaluator(plan, takes, x, dd), x)
+            self._test_eval = (key, ConstraintEvaluator(plan, takes, x, dd, activation_cache=False), x)
         _, ev, x = self._test_eval
         with torch.no_grad():
             u = ev.forward(self.params)

@@ -112,6 +112,11 @@ int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode);
 /* Scratch floats the generic kernels need per pair (0 for tiled plans in auto mode). */
 int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan);
+/* Floats per pair of the optional activation cache (0 if the plan's kernels do not use one).  When a cache of
+ * s * that many floats is passed to fbp_forward, the tiled forward kernel saves the jets of the last hidden layer
+ * in it and fbp_backward (given the same buffer, same parameters) loads them back with TMA bulk copies instead of
+ * recomputing the hidden-layer GEMM: a deliberate trade of idle HBM bandwidth for FP32 work. */
+int64_t fbp_plan_cache_per_pair(const fbp_plan* plan);
 
 /* ---- parameter packing: reference pytree leaves <-> [m][P] (leaves: "layers" list of (w (m,out,in),
  *      b (m,out)), fbpinns/networks.py:43-47 vmapped at fbpinns/trainers.py:603-607) ------------ */
@@ -157,10 +162,10 @@ int fbp_window_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float*
 
 /* Per-pair numerator jets N_c = d^c(u_i * w_i): norm -> FCN jets -> unnorm -> window jets -> Leibniz.
  * (FBPINN_model_inner under the nested jvp, fbpinns/trainers.py:113-118, 213-247).
- * d_pair_out [s][C*ud] in subdomain-sorted order; d_scratch only for generic plans. */
+ * d_pair_out [s][C*ud] in subdomain-sorted order; d_scratch only for generic plans; d_act_cache optional (NULL). */
 int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                 const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats,
-                void* stream);
+                float* d_act_cache, void* stream);
 
 /* Segment sums + partition-of-unity quotient + /npou (fbpinns/trainers.py:163-170) applied to jets:
  * per row N = sum of its pairs in REFERENCE order, jets of N/D by the quotient rule, summed over the
@@ -182,7 +187,7 @@ int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const fl
 int64_t fbp_backward_workspace_floats(const fbp_plan* plan, const fbp_takes_view* tv);
 int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                  const float* d_sub_static, const float* d_grow, float* d_grads, int32_t accumulate,
-                 float* d_gpart, float* d_scratch, int64_t scratch_floats, void* stream);
+                 float* d_gpart, float* d_scratch, int64_t scratch_floats, const float* d_act_cache, void* stream);
 
 /* optax.adam + apply_updates (fbpinns/trainers.py:294-295, 430) on rows of [.][P]:
  * for i < n_rows: row r = d_row_ids ? d_row_ids[i] : i of d_params/d_mu/d_nu; gradient row i of d_grads.

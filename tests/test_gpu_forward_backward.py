@@ -182,3 +182,38 @@ def test_partition_of_unity_property_full_size():
         for c_ in range(u_gen.shape[1]):
             e = common.rel_err(u_fast[:, c_].cpu().numpy(), u_gen[:, c_].cpu().numpy())
             assert e < TOL, (c_, e)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg4", "cfg5"])
+def test_activation_cache_matches_recompute(name):
+    """tiled reverse kernel: TMA-loaded activation cache (forward saves the hidden jets) vs recompute path — same
+    gradients up to float32 summation order (both are checked against the oracle elsewhere)."""
+    import gpu_common
+    from fbpinns_b200.engine import ConstraintEvaluator
+    small = dict(configs.SMALL[name])
+    if name == "cfg5":
+        small.update(n_sub=(5, 4), n_pts=(160, 136))      # full 128-point tiles + partial tails in every subdomain
+    k = common.make_case(configs.CONFIGS[name](**small), seed=4)
+    dd, inp, params = gpu_common.device_case(k, kernel="auto")
+    ev = inp.evaluators[0]
+    assert ev.plan.is_fast and ev.cache is not None and ev.plan.cache_per_pair > 0
+    ev2 = ConstraintEvaluator(ev.plan, ev.takes, ev.x, dd, activation_cache=False)
+    assert ev2.cache is None
+    torch.manual_seed(0)
+    ubar = torch.randn(ev.takes.n, ev.V, device=params.device)
+    m_act = max(len(inp.active_ims), 1)
+    g1 = torch.zeros((m_act, params.shape[1]), device=params.device)
+    g2 = torch.zeros_like(g1)
+    u1 = ev.forward(params)
+    ev.backward(ubar, params, g1, accumulate=False)
+    u2 = ev2.forward(params)
+    ev2.backward(ubar, params, g2, accumulate=False)
+    torch.cuda.synchronize()
+    assert torch.equal(u1, u2)
+    assert torch.isfinite(g1).all()
+    assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 2e-6
+    # a second step with different parameters must refresh the cache (no stale activations)
+    p2 = params * 1.01
+    ev.forward(p2); ev.backward(ubar, p2, g1, accumulate=False)
+    ev2.forward(p2); ev2.backward(ubar, p2, g2, accumulate=False)
+    assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 2e-6

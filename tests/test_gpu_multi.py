@@ -47,10 +47,13 @@ def _worker(rank, world, port, name, q):
         q.put((rank, ref_losses, out))
         dist.barrier()
         torch.cuda.synchronize()
-    finally:
-        import time
-        time.sleep(1.0)          # let the queue feeder thread flush
-        os._exit(0)              # NCCL teardown with captured graphs alive can hang (see bench.py)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    import time
+    time.sleep(1.0)              # let the queue feeder thread flush
+    os._exit(0)                  # NCCL teardown with captured graphs alive can hang (see bench.py)
 
 
 @pytest.mark.parametrize("name", ["cfg5", "cfg3", "cfg2"])
