@@ -15,7 +15,8 @@ FBP_MAX_UD = 4
 FBP_MAX_COMP = 10
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfbpinn_b200.so")
+# FBP_LIB selects a differently-tuned build of the same library (A/B experiments); the default is the product build
+LIB_PATH = os.environ.get("FBP_LIB") or os.path.join(_HERE, "csrc", "libfbpinn_b200.so")
 
 
 class FbpError(RuntimeError):

@@ -77,7 +77,10 @@ struct FastCfg {
     static constexpr int bwd_floats(int tp) {
         return SM_PARAMS + SM_GRAD + 3 * tp + C * tp + NHID * H * (C * tp + 4);
     }
-    static constexpr bool bwd_ok(int tp) { return bwd_floats(tp) * 4 <= 200 * 1024 && JG * (tp / PPT) <= 256; }
+#ifndef FBP_TPB_CAP
+#define FBP_TPB_CAP 128
+#endif
+    static constexpr bool bwd_ok(int tp) { return tp <= FBP_TPB_CAP && bwd_floats(tp) * 4 <= 200 * 1024 && JG * (tp / PPT) <= 256; }
     static constexpr int TPB = bwd_ok(128) ? 128 : (bwd_ok(64) ? 64 : 32);
     static constexpr int NTB = JG * (TPB / PPT);
 };
@@ -108,6 +111,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void tma_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // generic-proxy accesses to shared memory before this fence are ordered before later async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -314,8 +323,10 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
     const int jg = tid / (TP / PPT), pp = tid % (TP / PPT);
     const int j0 = jg * TM, p0 = pp * PPT;
 
+    constexpr bool TMA_SAVE = (CF::NHID == 2) && (CF::TPF == CF::TPB);   // forward tile == reverse tile: bulk stores
     for (int t0 = 0; t0 < count; t0 += TP) {
         const int cnt = min(TP, count - t0);
+        if (TMA_SAVE && tid == 0) tma_store_wait_read();     // previous tile's bulk stores have read `act`
         if (tid < TP) {
             const int pt = a.spair_point[first + t0 + (tid < cnt ? tid : 0)];
 #pragma unroll
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
                     fast_tanh_jets<CF>(acc[j][p]);
                 }
             }
-            if (a.cache != nullptr) {
+            if (a.cache != nullptr && !(TMA_SAVE && cnt == TP)) {
                 // save the hidden jets for the reverse kernel in ITS tile layout: [H][C][cntb] at (first+t0b)*H*C
                 constexpr int TPB = CF::TPB;
                 const int off = t0 + p0;                         // pair offset inside the work item (even)
@@ -378,6 +389,8 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
             *reinterpret_cast<float2*>(part + (jg * C + c) * TP + p0) = make_float2(s0, s1);
         }
         __syncthreads();
+        const bool bulk_save = TMA_SAVE && a.cache != nullptr && cnt == TP;
+        if (bulk_save) fast_store_act<CF, TP, RS>(act, j0, p0, acc);   // every GEMM read of act is done: h1 over h0
 
         if (tid < TP) {
             float u[C];
@@ -407,16 +420,25 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
             }
         }
         __syncthreads();
+        if (bulk_save && tid == 0) {
+            // the tile's [H][C][TP] block is contiguous both in shared memory and in the cache: H bulk stores
+            fence_proxy_async();
+            float* cdst = a.cache + (int64_t)(first + t0) * (H * C);
+            for (int k = 0; k < H; ++k) tma_bulk_s2g(cdst + k * RS, act + k * RS, (uint32_t)(RS * sizeof(float)));
+            tma_store_commit();
+        }
         float* dst = a.pair_out + (int64_t)(first + t0) * C;
         for (int i = tid; i < cnt * C; i += NT) dst[i] = outN[i];
     }
+    if (TMA_SAVE && tid == 0) tma_store_wait_read();
 }
 
 // =====================================================================================================
 // reverse
 // =====================================================================================================
 template <class CF, bool USE_CACHE>
-__global__ void __launch_bounds__(CF::NTB, 1) fast_backward_kernel(FastArgs a) {
+__global__ void __launch_bounds__(CF::NTB, (CF::bwd_floats(CF::TPB) * 4 <= 110 * 1024 && CF::NTB <= 128) ? 2 : 1)
+fast_backward_kernel(FastArgs a) {
     constexpr int H = CF::H, C = CF::C, TM = CF::TM, PPT = CF::PPT, JG = CF::JG, TP = CF::TPB, NT = CF::NTB;
     constexpr int NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
     constexpr int RS = C * TP + 4;

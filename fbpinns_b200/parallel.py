@@ -251,10 +251,12 @@ def make_sharded_update(base_cls):
         def forward_loss(self):
             self._refresh_problem_views()
             cons = []
-            for sev, con, w in zip(self.inp.evaluators, self.inp.constraints, self.inp.weights):
+            for sev, con, w, aff in zip(self.inp.evaluators, self.inp.constraints, self.inp.weights, self.affine):
                 ujets = sharded_sum(sev, self.params, self.grads, self.hook, w)
                 jet = sev.ev.plan.jet
-                if self.has_constraining:
+                if aff is not None:
+                    ujs = aff.ujs(ujets)
+                elif self.has_constraining:
                     ujs = jet.ujs_constrained(ujets, con[0], self.problem.constraining_fn, self.all_params)
                 else:
                     ujs = jet.ujs_plain(ujets)

@@ -22,7 +22,7 @@ import torch
 from . import networks, decompositions
 from .engine import (Plan, DeviceTakes, ConstraintEvaluator, PackedAdam, pack_params, unpack_params,
                      subdomain_sum, gather_rows, nonzero_i32, device_info)
-from .jets import JetSpec, get_jmaps  # noqa: F401  (get_jmaps re-exported: reference API name)
+from .jets import JetSpec, AffineConstraining, get_jmaps  # noqa: F401  (get_jmaps: reference API name)
 from .util.logger import logger
 
 
@@ -119,6 +119,15 @@ class UpdateStep:
         self.graph = None
         self.n_eager = 0
         self.kernel_launches_per_step = None
+        # constraining operators that are affine in u (all hard-BC ansatzes of the reference problems) get static
+        # coefficient jets, computed once here; anything else goes through the generic nested-jvp path every step
+        self.affine = []
+        for ev, con in zip(inputs.evaluators, inputs.constraints):
+            jet = (ev.ev if hasattr(ev, "ev") else ev).plan.jet
+            aff = None
+            if self.has_constraining and prob_flat is None:
+                aff = AffineConstraining.build(jet, con[0], problem.constraining_fn, all_params)
+            self.affine.append(aff)
 
     def _refresh_problem_views(self):
         "problem trainables are views of one flat leaf (rebuilt per step so that every tape is fresh)"
@@ -131,10 +140,12 @@ class UpdateStep:
     def forward_loss(self):
         self._refresh_problem_views()
         cons = []
-        for ev, con in zip(self.inp.evaluators, self.inp.constraints):
+        for ev, con, aff in zip(self.inp.evaluators, self.inp.constraints, self.affine):
             ujets = subdomain_sum(ev, self.params, self.grads, self.hook)
             jet = ev.plan.jet
-            if self.has_constraining:
+            if aff is not None:
+                ujs = aff.ujs(ujets)
+            elif self.has_constraining:
                 ujs = jet.ujs_constrained(ujets, con[0], self.problem.constraining_fn, self.all_params)
             else:
                 ujs = jet.ujs_plain(ujets)

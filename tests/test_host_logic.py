@@ -195,3 +195,34 @@ def test_every_baseline_config_has_a_tiled_kernel_instance():
         assert Plan(ls, JetSpec(((0, (0, 0)), (0, (1, 1))), 2, 1)).is_fast
     assert not Plan([2, 24, 1], JetSpec(((0, ()),), 2, 1)).is_fast     # falls back to the generic family
     assert not Plan([2, 32, 32, 32, 1], JetSpec(((0, ()),), 2, 1)).is_fast
+
+
+def test_affine_constraining_fast_path_matches_generic():
+    "A(x) u + B(x) detection + Leibniz on static coefficient jets == nested-jvp path (values and reverse mode)"
+    from fbpinns_b200.jets import AffineConstraining
+    from fbpinns_b200 import problems as P
+    torch.manual_seed(0)
+    cases = [(P.BurgersEquation2D, 2, ((0, ()), (0, (0,)), (0, (1,)), (0, (0, 0)))),
+             (P.WaveEquationGaussianVelocity3D, 3, ((0, (0, 0)), (0, (1, 1)), (0, (2, 2)))),
+             (P.HarmonicOscillator1DHardBC, 1, ((0, ()), (0, (0,)), (0, (0, 0)))),
+             (P.Poisson2D, 2, ((0, (0, 0)), (0, (1, 1))))]
+    for prob, xd, req in cases:
+        sp, _ = prob.init_params()
+        ap = {"static": {"problem": {k: (v.double() if torch.is_tensor(v) else v) for k, v in sp.items()}}, "trainable": {}}
+        x = torch.rand(23, xd, dtype=torch.float64) * 0.8 + 0.1
+        jet = JetSpec(req, xd, 1)
+        aff = AffineConstraining.build(jet, x, prob.constraining_fn, ap)
+        assert aff is not None, prob
+        uj = torch.randn(23, jet.C, dtype=torch.float64, requires_grad=True)
+        got = aff.ujs(uj)
+        ref = jet.ujs_constrained(uj, x, prob.constraining_fn, ap)
+        w = [torch.randn_like(r) for r in ref]
+        for a, b in zip(got, ref):
+            assert torch.allclose(a, b, rtol=1e-9, atol=1e-9)
+        g1, = torch.autograd.grad(sum((a * ww).sum() for a, ww in zip(got, w)), uj)
+        g2, = torch.autograd.grad(sum((b * ww).sum() for b, ww in zip(ref, w)), uj)
+        assert torch.allclose(g1, g2, rtol=1e-9, atol=1e-9)
+    # a non-affine operator must be rejected (-> generic path)
+    nonaff = lambda ap, x, u: torch.tanh(x[:, 0:1]) * u ** 2
+    x = torch.rand(11, 1, dtype=torch.float64)
+    assert AffineConstraining.build(JetSpec(((0, ()), (0, (0,))), 1, 1), x, nonaff, {}) is None
