@@ -264,7 +264,7 @@ def run_ours(args):
         check(lib.fbp_forward(ev.plan.handle, Cc.byref(tv), ptr(ev.x), ptr(tr.params), ptr(tr.dd.sub_static),
                               ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, ptr(ev.cache), stream_ptr()), "fbp_forward")
 
-    check(lib.fbp_reduce_backward(ev.plan.handle, Cc.byref(tv), ptr(ubar), ptr(ev.dsum), ptr(ev.grow), stream_ptr()), "rb")
+    check(lib.fbp_reduce_backward(ev.plan.handle, Cc.byref(tv), ptr(ubar), ptr(ev.dsum), None, ptr(ev.grow), stream_ptr()), "rb")
 
     def k_bwd():
         check(lib.fbp_backward(ev.plan.handle, Cc.byref(tv), ptr(ev.x), ptr(tr.params), ptr(tr.dd.sub_static), ptr(ev.grow),

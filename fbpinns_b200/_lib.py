@@ -37,6 +37,7 @@ class TakesView(C.Structure):
                 ("d_sub_off", C.c_void_p), ("d_spair_point", C.c_void_p), ("d_spair_row", C.c_void_p),
                 ("d_spair_sub", C.c_void_p), ("d_pos", C.c_void_p), ("d_row_off", C.c_void_p),
                 ("d_pt_row_off", C.c_void_p), ("d_items", C.c_void_p), ("d_sub_item_off", C.c_void_p),
+                ("d_item_order_fwd", C.c_void_p), ("d_item_order_bwd", C.c_void_p),
                 ("n_items", C.c_int32), ("n_items_active", C.c_int32)]
 
 
@@ -68,10 +69,10 @@ SIGNATURES = {
     "fbp_takes_destroy": (C.c_int, [_P]),
     "fbp_window_sums": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
     "fbp_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I64, _P, _P]),
-    "fbp_reduce_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
-    "fbp_reduce_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
+    "fbp_reduce_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P]),
+    "fbp_reduce_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P]),
     "fbp_row_sums": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P]),
-    "fbp_reduce_rows_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P]),
+    "fbp_reduce_rows_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P]),
     "fbp_backward_workspace_floats": (_I64, [_P, C.POINTER(TakesView)]),
     "fbp_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _P]),
     "fbp_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I32, _F, _F, _F, _F, _F, _P]),

@@ -59,7 +59,7 @@ static void fill_args(const fbp_plan* plan, const fbp_takes_view* tv, const floa
                       const float* d_sub_static, FastArgs& a) {
     a.x = d_x; a.params = d_params; a.sub_static = d_sub_static;
     a.sub_ids = tv->d_sub_ids; a.spair_point = tv->d_spair_point; a.spair_row = tv->d_spair_row; a.items = tv->d_items;
-    a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr; a.cache = nullptr;
+    a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr; a.cache = nullptr; a.order = nullptr;
     a.xd = plan->dev.xd; a.P = plan->dev.P;
     for (int i = 0; i < FBP_MAX_XD; ++i) a.axis[i] = plan->fast.axis[i];
     for (int i = 0; i < FBP_MAX_COMP; ++i) a.ext[i] = plan->fast.ext[i];
@@ -84,6 +84,7 @@ int fbp_fast_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float
     fill_args(plan, tv, d_x, d_params, d_sub_static, a);
     a.pair_out = d_pair_out;
     a.cache = d_cache;
+    a.order = tv->d_item_order_fwd;
     return dispatch(plan, false, a, tv->n_items, stream);
 }
 
@@ -102,6 +103,7 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
         a.grow = d_grow;
         a.gpart = d_gpart;
         a.cache = const_cast<float*>(d_cache);
+        a.order = tv->d_item_order_bwd;
         if (int rc = dispatch(plan, true, a, tv->n_items_active, stream)) return rc;
     }
     const int64_t total = (int64_t)tv->m_active * plan->dev.P;

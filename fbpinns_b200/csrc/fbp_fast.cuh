@@ -32,6 +32,7 @@ struct FastArgs {
     const int32_t* spair_point;
     const int32_t* spair_row;
     const int32_t* items;
+    const int32_t* order;   // optional launch order: block b works on item order[b] (longest first)
     float* pair_out;     // forward output  [s][C]
     const float* grow;   // reverse input   [q][C]
     float* gpart;        // reverse output  [n_items_active][P]
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
     float* outN = part + JG * C * TP;                     // [TP][C] in external component order
 
     const int tid = threadIdx.x;
-    const int item = blockIdx.x;
+    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
     const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
     const int im = a.sub_ids[sp];
     const int xd = a.xd;
@@ -466,7 +467,7 @@ fast_backward_kernel(FastArgs a) {
     constexpr uint32_t ROW_BYTES = C * TP * sizeof(float);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int item = blockIdx.x;
+    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
     const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
     const int im = a.sub_ids[sp];
     const int xd = a.xd;

@@ -61,7 +61,7 @@ row_sums_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_ou
 template <bool FROM_ROWS>
 __global__ void __launch_bounds__(RT)
 reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_out,
-                      const float* __restrict__ dsum, float* __restrict__ ujets) {
+                      const float* __restrict__ dsum, const float* __restrict__ aff, float* __restrict__ ujets) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= tv.n) return;
     const int C = pd.C, ud = pd.ud, V = C * ud;
@@ -93,13 +93,27 @@ reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ p
         }
     }
     const float npou = (float)tv.npou;
-    for (int v = 0; v < V; ++v) ujets[p * V + v] = acc[v] / npou;
+    for (int v = 0; v < V; ++v) acc[v] = acc[v] / npou;
+    if (aff != nullptr) {
+        // constraining operator A(x) u + B(x): Leibniz rule on the jets (ud == 1, checked by the launcher)
+        const float* A = aff + p * (2 * C);
+        const float* B = A + C;
+        float o[FBP_MAX_COMP];
+        for (int c = 0; c < C; ++c) {
+            float v = A[c] * acc[0] + B[c];
+            if (pd.ord[c] == 1) v += A[0] * acc[c];
+            else if (pd.ord[c] == 2) v += A[pd.i1[c]] * acc[pd.i2[c]] + A[pd.i2[c]] * acc[pd.i1[c]] + A[0] * acc[c];
+            o[c] = v;
+        }
+        for (int c = 0; c < C; ++c) acc[c] = o[c];
+    }
+    for (int v = 0; v < V; ++v) ujets[p * V + v] = acc[v];
 }
 
 // ---- transpose: grow[r] = A(D_r)^T ujets_bar[point(r)] / npou ---------------------------------------
 __global__ void __launch_bounds__(RT)
 reduce_backward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ ubar_in,
-                       const float* __restrict__ dsum, float* __restrict__ grow) {
+                       const float* __restrict__ dsum, const float* __restrict__ aff, float* __restrict__ grow) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= tv.q) return;
     const int C = pd.C, ud = pd.ud, V = C * ud;
@@ -110,7 +124,24 @@ reduce_backward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ 
     const float npou = (float)tv.npou;
     for (int o = 0; o < ud; ++o) {
         float ub[FBP_MAX_COMP], nb[FBP_MAX_COMP];
-        for (int c = 0; c < C; ++c) ub[c] = ubar_in[(int64_t)pt * V + c * ud + o] / npou;
+        if (aff != nullptr) {
+            // transpose of the Leibniz rule of the constraining operator (ud == 1)
+            const float* A = aff + (int64_t)pt * (2 * C);
+            float cb[FBP_MAX_COMP];
+            for (int c = 0; c < C; ++c) { cb[c] = ubar_in[(int64_t)pt * V + c]; ub[c] = 0.0f; }
+            for (int c = 0; c < C; ++c) {
+                ub[0] += cb[c] * A[c];
+                if (pd.ord[c] == 1) ub[c] += cb[c] * A[0];
+                else if (pd.ord[c] == 2) {
+                    ub[c] += cb[c] * A[0];
+                    ub[pd.i1[c]] += cb[c] * A[pd.i2[c]];
+                    ub[pd.i2[c]] += cb[c] * A[pd.i1[c]];
+                }
+            }
+            for (int c = 0; c < C; ++c) ub[c] = ub[c] / npou;
+        } else {
+            for (int c = 0; c < C; ++c) ub[c] = ubar_in[(int64_t)pt * V + c * ud + o] / npou;
+        }
         for (int c = 1; c < C; ++c)
             if (pd.ord[c] == 2) {
                 float t = ub[c] * invD;
@@ -213,10 +244,11 @@ int fbp_window_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float*
 }
 
 int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out, const float* d_dsum,
-                       float* d_ujets, void* stream) {
+                       const float* d_affine, float* d_ujets, void* stream) {
     FBP_REQUIRE(plan && tv, "fbp_reduce_forward: null plan/takes");
+    FBP_REQUIRE(d_affine == nullptr || plan->dev.ud == 1, "fbp_reduce_forward: affine constraining needs ud == 1");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<false><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_ujets);
+    reduce_forward_kernel<false><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_affine, d_ujets);
     FBP_LAUNCH_CHECK();
     return 0;
 }
@@ -230,19 +262,22 @@ int fbp_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_
 }
 
 int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_nsum, const float* d_dsum,
-                            float* d_ujets, void* stream) {
+                            const float* d_affine, float* d_ujets, void* stream) {
     FBP_REQUIRE(plan && tv, "fbp_reduce_rows_forward: null plan/takes");
+    FBP_REQUIRE(d_affine == nullptr || plan->dev.ud == 1, "fbp_reduce_rows_forward: affine constraining needs ud == 1");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<true><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_nsum, d_dsum, d_ujets);
+    reduce_forward_kernel<true><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_nsum, d_dsum, d_affine, d_ujets);
     FBP_LAUNCH_CHECK();
     return 0;
 }
 
 int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_ujets_bar, const float* d_dsum,
-                        float* d_grow, void* stream) {
+                        const float* d_affine, float* d_grow, void* stream) {
     FBP_REQUIRE(plan && tv, "fbp_reduce_backward: null plan/takes");
+    FBP_REQUIRE(d_affine == nullptr || (plan->dev.ud == 1 && tv->npou == 1),
+                "fbp_reduce_backward: affine constraining needs ud == 1 and a single partition of unity");
     if (tv->q == 0) return 0;
-    reduce_backward_kernel<<<blocks_for(tv->q, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_ujets_bar, d_dsum, d_grow);
+    reduce_backward_kernel<<<blocks_for(tv->q, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_ujets_bar, d_dsum, d_affine, d_grow);
     FBP_LAUNCH_CHECK();
     return 0;
 }

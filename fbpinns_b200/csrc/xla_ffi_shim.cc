@@ -32,7 +32,7 @@ static ffi::Error ForwardImpl(cudaStream_t stream, int64_t plan, int64_t takes, 
     auto* tv = reinterpret_cast<const fbp_takes_view*>(takes);
     int rc = fbp_forward(p, tv, x.typed_data(), params.typed_data(), sub_static.typed_data(), pair_out->typed_data(),
                          nullptr, 0, /*d_act_cache=*/nullptr, stream);
-    if (rc == 0) rc = fbp_reduce_forward(p, tv, pair_out->typed_data(), dsum.typed_data(), ujets->typed_data(), stream);
+    if (rc == 0) rc = fbp_reduce_forward(p, tv, pair_out->typed_data(), dsum.typed_data(), /*d_affine=*/nullptr, ujets->typed_data(), stream);
     return status(rc);
 }
 
@@ -44,7 +44,7 @@ static ffi::Error BackwardImpl(cudaStream_t stream, int64_t plan, int64_t takes,
                                ffi::ResultBuffer<ffi::F32> grads) {
     auto* p = reinterpret_cast<const fbp_plan*>(plan);
     auto* tv = reinterpret_cast<const fbp_takes_view*>(takes);
-    int rc = fbp_reduce_backward(p, tv, ujets_bar.typed_data(), dsum.typed_data(), grow->typed_data(), stream);
+    int rc = fbp_reduce_backward(p, tv, ujets_bar.typed_data(), dsum.typed_data(), /*d_affine=*/nullptr, grow->typed_data(), stream);
     if (rc == 0)
         rc = fbp_backward(p, tv, x.typed_data(), params.typed_data(), sub_static.typed_data(), grow->typed_data(),
                           grads->typed_data(), /*accumulate=*/0, gpart->typed_data(), nullptr, 0, /*d_act_cache=*/nullptr, stream);

@@ -158,27 +158,34 @@ def gather_rows(src, idx):
 
 def build_work_items(sub_off, m_active, tile_points, target_items):
     """Work list for the tiled kernels: (subdomain position, first pair, pair count, split index) rows, subdomain
-    major.  A subdomain is split into chunks of a whole number of tiles so that the list has about
-    `target_items` entries when the problem is small, and one entry per subdomain when it is large."""
+    major.  A subdomain is cut into equal chunks (whole numbers of tiles) so that the list has about `target_items`
+    entries when the problem is small and one entry per subdomain when it is large.  Also returns the launch orders
+    (longest item first, LPT) for the forward (all items) and reverse (active items) kernels."""
     sub_off = np.asarray(sub_off, dtype=np.int64)
     m_all = len(sub_off) - 1
     s = int(sub_off[-1])
-    chunk = max(1, -(-s // max(1, target_items)))
-    chunk = -(-chunk // tile_points) * tile_points
+    chunk0 = max(1, -(-s // max(1, target_items)))
+    chunk0 = -(-chunk0 // tile_points) * tile_points
     items, sub_item_off = [], [0]
     for sp in range(m_all):
         a, b = int(sub_off[sp]), int(sub_off[sp + 1])
-        k = 0
-        while a < b:
-            c = min(chunk, b - a)
-            items.append((sp, a, c, k))
-            a += c
-            k += 1
+        cnt = b - a
+        if cnt > 0:
+            parts = -(-cnt // chunk0)
+            size = -(-(-(-cnt // parts)) // tile_points) * tile_points      # equal parts, rounded up to whole tiles
+            k = 0
+            while a < b:
+                c = min(size, b - a)
+                items.append((sp, a, c, k))
+                a += c
+                k += 1
         sub_item_off.append(len(items))
     items = np.asarray(items, dtype=np.int32).reshape(-1, 4)
     sub_item_off = np.asarray(sub_item_off, dtype=np.int32)
     n_items_active = int(sub_item_off[m_active])
-    return items, sub_item_off, n_items_active
+    order_fwd = np.argsort(-items[:, 2], kind="stable").astype(np.int32)
+    order_bwd = np.argsort(-items[:n_items_active, 2], kind="stable").astype(np.int32)
+    return items, sub_item_off, n_items_active, order_fwd, order_bwd
 
 
 class DeviceTakes:
@@ -219,11 +226,14 @@ class DeviceTakes:
     def set_tiling(self, tile_points, target_items=None):
         if target_items is None:
             target_items = 8 * device_info()["sm_count"]
-        items, sub_item_off, nia = build_work_items(self.sub_off_host, self.m_active, tile_points, target_items)
+        items, sub_item_off, nia, order_fwd, order_bwd = build_work_items(self.sub_off_host, self.m_active, tile_points,
+                                                                          target_items)
         dev = self.sub_ids.device
         self.items_host = items
         self.items = torch.as_tensor(items.reshape(-1), dtype=I32, device=dev)
         self.sub_item_off = torch.as_tensor(sub_item_off, dtype=I32, device=dev)
+        self.item_order_fwd = torch.as_tensor(order_fwd, dtype=I32, device=dev)
+        self.item_order_bwd = torch.as_tensor(order_bwd, dtype=I32, device=dev)
         self.n_items, self.n_items_active = int(items.shape[0]), nia
         self.tile_points = tile_points
         self._view = None
@@ -237,7 +247,8 @@ class DeviceTakes:
                             ("d_sub_off", self.sub_off), ("d_spair_point", self.spair_point),
                             ("d_spair_row", self.spair_row), ("d_spair_sub", self.spair_sub), ("d_pos", self.pos),
                             ("d_row_off", self.row_off), ("d_pt_row_off", self.pt_row_off), ("d_items", self.items),
-                            ("d_sub_item_off", self.sub_item_off)]:
+                            ("d_sub_item_off", self.sub_item_off), ("d_item_order_fwd", self.item_order_fwd),
+                            ("d_item_order_bwd", self.item_order_bwd)]:
                 setattr(v, name, t.data_ptr() if t.numel() else None)
             v.n_items, v.n_items_active = self.n_items, self.n_items_active
             self._view = v
@@ -281,19 +292,25 @@ class ConstraintEvaluator:
         # layer's jets, the reverse kernel TMA-loads them instead of recomputing the hidden GEMM
         ncache = takes.s * plan.cache_per_pair if activation_cache else 0
         self.cache = torch.zeros(ncache, dtype=torch.float32, device=dev) if ncache else None
+        self.affine = None      # optional (n, 2C): jets of A and B of an affine constraining operator (set_affine)
         check(lib.fbp_window_sums(plan.handle, C.byref(takes.view()), ptr(self.x), ptr(decomp.sub_static),
                                   ptr(self.dsum), stream_ptr()), "fbp_window_sums")
 
+    def set_affine(self, aff):
+        "fuse the constraining operator A(x) u + B(x) (jets.AffineConstraining) into the reduce kernels"
+        self.affine = None if aff is None else torch.cat([aff.Aj, aff.Bj], dim=1).contiguous().float()
+
     def forward(self, params):
-        """params: packed (m, P) -> ujets (n, C*ud) of the unconstrained subdomain sum."""
+        """params: packed (m, P) -> ujets (n, C*ud) of the subdomain sum (of the CONSTRAINED solution when an affine
+        constraining operator has been attached with set_affine)."""
         lib = _lib.load()
         tv = self.takes.view()
         check(lib.fbp_forward(self.plan.handle, C.byref(tv), ptr(self.x), ptr(params), ptr(self.decomp.sub_static),
                               ptr(self.pair_out), ptr(self.scratch), self.scratch_floats, ptr(self.cache), stream_ptr()),
               "fbp_forward")
         ujets = torch.empty((self.takes.n, self.V), dtype=torch.float32, device=self.x.device)
-        check(lib.fbp_reduce_forward(self.plan.handle, C.byref(tv), ptr(self.pair_out), ptr(self.dsum), ptr(ujets),
-                                     stream_ptr()), "fbp_reduce_forward")
+        check(lib.fbp_reduce_forward(self.plan.handle, C.byref(tv), ptr(self.pair_out), ptr(self.dsum), ptr(self.affine),
+                                     ptr(ujets), stream_ptr()), "fbp_reduce_forward")
         return ujets
 
     def backward(self, ujets_bar, params, grads, accumulate=True):
@@ -301,8 +318,8 @@ class ConstraintEvaluator:
         lib = _lib.load()
         tv = self.takes.view()
         ub = ujets_bar.contiguous().float()
-        check(lib.fbp_reduce_backward(self.plan.handle, C.byref(tv), ptr(ub), ptr(self.dsum), ptr(self.grow),
-                                      stream_ptr()), "fbp_reduce_backward")
+        check(lib.fbp_reduce_backward(self.plan.handle, C.byref(tv), ptr(ub), ptr(self.dsum), ptr(self.affine),
+                                      ptr(self.grow), stream_ptr()), "fbp_reduce_backward")
         check(lib.fbp_backward(self.plan.handle, C.byref(tv), ptr(self.x), ptr(params), ptr(self.decomp.sub_static),
                                ptr(self.grow), ptr(grads), 1 if accumulate else 0, ptr(self.gpart), ptr(self.scratch),
                                self.scratch_floats, ptr(self.cache), stream_ptr()), "fbp_backward")

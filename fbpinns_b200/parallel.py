@@ -136,8 +136,8 @@ class ShardedEvaluator:
         check(lib.fbp_row_sums(ev.plan.handle, C.byref(tv), ptr(ev.pair_out), ptr(self.nsum), stream_ptr()), "fbp_row_sums")
         self.halo.forward_add(self.nsum)
         ujets = torch.empty((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
-        check(lib.fbp_reduce_rows_forward(ev.plan.handle, C.byref(tv), ptr(self.nsum), ptr(ev.dsum), ptr(ujets),
-                                          stream_ptr()), "fbp_reduce_rows_forward")
+        check(lib.fbp_reduce_rows_forward(ev.plan.handle, C.byref(tv), ptr(self.nsum), ptr(ev.dsum), ptr(ev.affine),
+                                          ptr(ujets), stream_ptr()), "fbp_reduce_rows_forward")
         return ujets.index_select(0, self.owned_idx)
 
     def backward(self, ujets_bar_owned, params, grads):
@@ -146,8 +146,8 @@ class ShardedEvaluator:
         tv = ev.takes.view()
         ub = torch.zeros((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
         ub.index_copy_(0, self.owned_idx, ujets_bar_owned.contiguous().float())
-        check(lib.fbp_reduce_backward(ev.plan.handle, C.byref(tv), ptr(ub), ptr(ev.dsum), ptr(ev.grow), stream_ptr()),
-              "fbp_reduce_backward")
+        check(lib.fbp_reduce_backward(ev.plan.handle, C.byref(tv), ptr(ub), ptr(ev.dsum), ptr(ev.affine), ptr(ev.grow),
+                                      stream_ptr()), "fbp_reduce_backward")
         self.halo.backward_return(ev.grow[:ev.takes.q])
         check(lib.fbp_backward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
                                ptr(ev.grow), ptr(grads), 1, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats,
@@ -255,7 +255,7 @@ def make_sharded_update(base_cls):
                 ujets = sharded_sum(sev, self.params, self.grads, self.hook, w)
                 jet = sev.ev.plan.jet
                 if aff is not None:
-                    ujs = aff.ujs(ujets)
+                    ujs = jet.ujs_plain(ujets)        # the kernels already returned the constrained jets
                 elif self.has_constraining:
                     ujs = jet.ujs_constrained(ujets, con[0], self.problem.constraining_fn, self.all_params)
                 else:
@@ -265,22 +265,19 @@ def make_sharded_update(base_cls):
 
         def _eager(self):
             self.grads.zero_()
-            if self.prob_flat is not None:
-                self.prob_flat.grad = None
             self.hook.grad = None
             loss = self.forward_loss()
             loss.backward()
             w0 = self.inp.weights[0]
-            pg = None
-            if self.prob_flat is not None and self.prob_flat.numel():
-                pg = self.prob_flat.grad if self.prob_flat.grad is not None else torch.zeros_like(self.prob_flat)
-                pg = pg * w0
-                dist.all_reduce(pg, group=self.shard.group)
+            pg = self.problem_grad()
             with torch.no_grad():
+                if pg is not None:
+                    pg = (pg * w0).contiguous()
+                    dist.all_reduce(pg, group=self.shard.group)
                 gl = (loss.detach() * w0).reshape(1)
                 dist.all_reduce(gl, group=self.shard.group)
                 self.adam.step(self.params, self.grads, self.active_ims_dev,
-                               self.prob_flat.data if pg is not None else None, pg)
+                               self.prob_flat if pg is not None else None, pg)
                 self.loss_out.copy_(gl[0])
             return self.loss_out
 

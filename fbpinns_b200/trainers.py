@@ -123,19 +123,32 @@ class UpdateStep:
         # coefficient jets, computed once here; anything else goes through the generic nested-jvp path every step
         self.affine = []
         for ev, con in zip(inputs.evaluators, inputs.constraints):
-            jet = (ev.ev if hasattr(ev, "ev") else ev).plan.jet
+            base = ev.ev if hasattr(ev, "ev") else ev             # sharded evaluators wrap the local one
             aff = None
-            if self.has_constraining and prob_flat is None:
-                aff = AffineConstraining.build(jet, con[0], problem.constraining_fn, all_params)
+            if self.has_constraining and prob_flat is None and base.takes.npou == 1:
+                aff = AffineConstraining.build(base.plan.jet, base.x, problem.constraining_fn, all_params)
+            base.set_affine(aff)            # fused into the reduce kernels (forward Leibniz rule and its transpose)
             self.affine.append(aff)
 
     def _refresh_problem_views(self):
-        "problem trainables are views of one flat leaf (rebuilt per step so that every tape is fresh)"
+        """Problem trainables live in one flat storage buffer (updated in place by Adam).  Every step aliases it with a
+        FRESH leaf created on the current stream — a persistent leaf would keep an AccumulateGrad node bound to the
+        stream it was first used on, which breaks CUDA-graph capture — and rebuilds the views user code reads."""
+        self._pf = None
+        if self.prob_flat is None:
+            return
+        self._pf = self.prob_flat.detach().requires_grad_(True)
         off = 0
         for k, shp in zip(self.prob_keys, self.prob_shapes):
             nel = int(np.prod(shp)) if len(shp) else 1
-            self.all_params["trainable"]["problem"][k] = self.prob_flat[off:off + nel].view(shp)
+            self.all_params["trainable"]["problem"][k] = self._pf[off:off + nel].view(shp)
             off += nel
+
+    def problem_grad(self):
+        "gradient of the flat problem-parameter buffer from the last backward (zeros if unused)"
+        if self._pf is None or self.prob_flat.numel() == 0:
+            return None
+        return self._pf.grad if self._pf.grad is not None else torch.zeros_like(self.prob_flat)
 
     def forward_loss(self):
         self._refresh_problem_views()
@@ -144,7 +157,7 @@ class UpdateStep:
             ujets = subdomain_sum(ev, self.params, self.grads, self.hook)
             jet = ev.plan.jet
             if aff is not None:
-                ujs = aff.ujs(ujets)
+                ujs = jet.ujs_plain(ujets)            # the kernels already returned the constrained jets
             elif self.has_constraining:
                 ujs = jet.ujs_constrained(ujets, con[0], self.problem.constraining_fn, self.all_params)
             else:
@@ -154,17 +167,13 @@ class UpdateStep:
 
     def _eager(self):
         self.grads.zero_()
-        if self.prob_flat is not None:
-            self.prob_flat.grad = None
         self.hook.grad = None
         loss = self.forward_loss()
         loss.backward()
-        pg = None
-        if self.prob_flat is not None and self.prob_flat.numel():
-            pg = self.prob_flat.grad if self.prob_flat.grad is not None else torch.zeros_like(self.prob_flat)
+        pg = self.problem_grad()
         with torch.no_grad():
             self.adam.step(self.params, self.grads, self.active_ims_dev,
-                           self.prob_flat.data if pg is not None else None, pg)
+                           self.prob_flat if pg is not None else None, pg)
             self.loss_out.copy_(loss.detach())
         return self.loss_out
 
@@ -181,8 +190,6 @@ class UpdateStep:
                     self._eager()
                 torch.cuda.current_stream().wait_stream(s)
                 return self.loss_out
-            if self.prob_flat is not None:
-                self.prob_flat.grad = None
             self.hook.grad = None
             from . import _lib
             n0 = _lib.load().fbp_launch_count()
@@ -280,7 +287,7 @@ class FBPINNTrainer(_Trainer):
         prob_keys = list(prob_tr.keys())
         if prob_keys:
             flat = torch.cat([prob_tr[k].reshape(-1).float() for k in prob_keys]).to(dev)
-            self.prob_flat = flat.clone().requires_grad_(True)
+            self.prob_flat = flat.clone()          # plain storage; every step aliases it with a fresh grad leaf
             off = 0
             for k in prob_keys:
                 nel = prob_tr[k].numel()

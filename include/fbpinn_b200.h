@@ -89,6 +89,8 @@ typedef struct fbp_takes_view {
     const int32_t* d_pt_row_off; /* [n+1] row range of each point */
     const int32_t* d_items;      /* [n_items][4] work list (sub position, first pair, pair count, split id) */
     const int32_t* d_sub_item_off;/* [m_all+1] item range of each subdomain position */
+    const int32_t* d_item_order_fwd; /* [n_items] launch order of the items (longest first), NULL = identity */
+    const int32_t* d_item_order_bwd; /* [n_items_active] launch order of the active items, NULL = identity */
     int32_t n_items;             /* built by the host from d_sub_off (fbp_plan_tile_points) */
     int32_t n_items_active;      /* leading items that belong to active subdomains */
 } fbp_takes_view;
@@ -169,17 +171,20 @@ int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x
 
 /* Segment sums + partition-of-unity quotient + /npou (fbpinns/trainers.py:163-170) applied to jets:
  * per row N = sum of its pairs in REFERENCE order, jets of N/D by the quotient rule, summed over the
- * point's rows, divided by npou.  d_ujets [n][C*ud] (points without any pair get 0). */
+ * point's rows, divided by npou.  d_ujets [n][C*ud] (points without any pair get 0).
+ * d_affine (optional, ud = 1): [n][2*C] jets of A then B of a constraining operator of the form
+ * constraining_fn(x, u) = A(x) u + B(x) (fbpinns/problems.py:193-199, 312-318, 381-398); when given, the kernel also
+ * applies the Leibniz rule so that d_ujets holds the jets of the CONSTRAINED solution (fbpinns/trainers.py:174). */
 int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out,
-                       const float* d_dsum, float* d_ujets, void* stream);
+                       const float* d_dsum, const float* d_affine, float* d_ujets, void* stream);
 /* The same in two steps, for the multi-GPU halo exchange: row sums d_nsum [q][C*ud] of the LOCAL pairs,
  * then — after the partial sums of rows shared with other ranks have been added — the quotient rule from row sums. */
 int fbp_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out, float* d_nsum, void* stream);
 int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_nsum, const float* d_dsum,
-                            float* d_ujets, void* stream);
+                            const float* d_affine, float* d_ujets, void* stream);
 /* Transpose of the above: cotangent of ujets [n][C*ud] -> cotangent of row numerators d_grow [q][C*ud]. */
 int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_ujets_bar,
-                        const float* d_dsum, float* d_grow, void* stream);
+                        const float* d_dsum, const float* d_affine, float* d_grow, void* stream);
 
 /* Reverse pass through the pairs of the ACTIVE subdomains: d_grads [m_active][P] (overwritten when
  * accumulate == 0, added to otherwise — several constraints share one gradient buffer).

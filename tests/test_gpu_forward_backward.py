@@ -63,7 +63,7 @@ def _make_step(k, inp, params, dev, graph=False):
     keys = list(k.prob_trainable.keys())
     prob_flat = None
     if keys:
-        prob_flat = torch.cat([torch.as_tensor(k.prob_trainable[kk], device=dev).reshape(-1) for kk in keys]).clone().requires_grad_(True)
+        prob_flat = torch.cat([torch.as_tensor(k.prob_trainable[kk], device=dev).reshape(-1) for kk in keys]).clone()
     adam = PackedAdam(k.m, params.shape[1], 0 if prob_flat is None else prob_flat.numel(), dev, learning_rate=1e-3)
     step = UpdateStep(inp, params, adam, all_params, prob_flat, k.c.problem, use_cuda_graph=graph)
     return step, adam, prob_flat
@@ -90,7 +90,7 @@ def test_loss_and_grads_match_oracle(name, kernel):
         assert ew < TOL and eb < TOL, f"{name} layer {l}: grad rel err W {ew:.2e} b {eb:.2e}"
     if prob_flat is not None:
         for i, kk in enumerate(k.prob_trainable):
-            e = common.rel_err(prob_flat.grad.cpu().numpy()[i], g_prob[kk])
+            e = common.rel_err(step.problem_grad().cpu().numpy()[i], g_prob[kk])
             assert e < TOL, f"problem param {kk}: {e:.2e}"
 
 
