@@ -49,7 +49,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception:
@@ -204,14 +204,15 @@ def run_ours(args):
     sampler = ClockSampler(local)
     n0 = lib.fbp_launch_count()
     barrier()
-    sampler.start()
+    if rank == 0:                   # one poller only: N concurrent nvidia-smi loops stall the driver and the ranks
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         loss_t = tr.step()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else {}
     ms = e0.elapsed_time(e1)
     t_ms = torch.tensor([ms], device=dev)
     if world > 1:
