@@ -77,6 +77,7 @@ SIGNATURES = {
     "fbp_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _P]),
     "fbp_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I32, _F, _F, _F, _F, _F, _P]),
     "fbp_fma_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
+    "fbp_ffma2_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
 }
 
 _lib = None

@@ -374,8 +374,10 @@ class PackedAdam:
                                 stream_ptr()), "fbp_adam_step")
 
 
-def fma_peak_tflops(iters=20000):
+def fma_peak_tflops(iters=20000, packed=False):
+    "FP32 FMA micro-benchmark: scalar FFMA, or the packed FFMA2 (fma.rn.f32x2) when packed=True"
     lib = _lib.load()
     v = C.c_float()
-    check(lib.fbp_fma_peak(iters, C.byref(v), stream_ptr()), "fbp_fma_peak")
+    fn = lib.fbp_ffma2_peak if packed else lib.fbp_fma_peak
+    check(fn(iters, C.byref(v), stream_ptr()), "fbp_fma_peak")
     return float(v.value)

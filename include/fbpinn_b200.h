@@ -205,6 +205,8 @@ int fbp_adam_step(float* d_params, float* d_mu, float* d_nu, const float* d_grad
 /* FP32 FMA pipe micro-benchmark used as the roofline denominator by bench.py: runs `iters` dependent-free
  * FFMA per thread on a full grid; returns achieved TFLOP/s through *tflops (synchronises). */
 int fbp_fma_peak(int32_t iters, float* tflops, void* stream);
+/* The same with the packed instruction fma.rn.f32x2 (SASS FFMA2, sm_100+): 16 FMAs per thread per iteration. */
+int fbp_ffma2_peak(int32_t iters, float* tflops, void* stream);
 
 #ifdef __cplusplus
 }
