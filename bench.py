@@ -174,7 +174,13 @@ def run_ours(args):
     kw = dict(n_sub=FULL["n_sub"], n_pts=FULL["n_pts"], layer_sizes=layer_sizes)
     if args.small:
         kw.update(n_sub=(16, 16), n_pts=(256, 256))
-    c = configs.cfg5_poisson(device=str(dev), use_cuda_graph=not args.no_graph, kernel=args.kernel, **kw)
+    if args.config == "cfg5":
+        c = configs.cfg5_poisson(device=str(dev), use_cuda_graph=not args.no_graph, kernel=args.kernel, **kw)
+    else:       # the other BASELINE configs at full size, all subdomains active (informational lines, not the headline)
+        extra = dict(line_scheduler=False) if args.config == "cfg3" else {}
+        c = configs.CONFIGS[args.config](device=str(dev), use_cuda_graph=not args.no_graph, kernel=args.kernel, **extra)
+        layer_sizes = tuple(c.network_init_kwargs["layer_sizes"])
+        kw["n_pts"] = c.ns[0]
     tr = FBPINNTrainer(c)
     if world > 1:
         from fbpinns_b200.parallel import shard_trainer
@@ -297,7 +303,11 @@ def run_ours(args):
     # algorithmic HBM bytes per step
     P = tr.params.shape[1]
     hbm_bytes = 4 * (takes.n * 2 + 2 * s_local + 2 * takes.n * C + takes.m_all * P * 10)
-    step_tf = 3.0 * f_fwd * s_local * world / (ms_per_step * 1e-3) / 1e12
+    step_flops = 0.0
+    for e_ in tr.inputs.evaluators:
+        e_ = e_.ev if hasattr(e_, "ev") else e_
+        step_flops += 3.0 * flops_per_pair(layer_sizes, e_.plan.jet.C) * e_.takes.s
+    step_tf = step_flops * world / (ms_per_step * 1e-3) / 1e12
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------------------
     cpu = None
@@ -313,13 +323,14 @@ def run_ours(args):
             "metric": "train_steps_per_sec", "value": steps_per_s, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.small else "SMALL cfg5 16x16 subdomains 256x256 grid (debug)",
+            "config": {"workload": (WORKLOAD if args.config == "cfg5" else f"{args.config} (BASELINE config, all subdomains active)")
+                       if not args.small else "SMALL cfg5 16x16 subdomains 256x256 grid (debug)",
                        "layers": list(layer_sizes), "subdomains": m, "points": n_points_global,
                        "pairs_this_rank": s_local, "parallelism": f"subdomain-slabs x{world}" if world > 1 else "single GPU",
                        "cuda_graph": tr.update.graph is not None, "kernel_family": "tiled" if ev.plan.is_fast else "generic",
                        "l2": "per-step working set (pair jets 175 MB + indices 105 MB) exceeds the 126 MB L2; "
                              "per-kernel timings flush L2 with a 256 MB write between launches"},
-            "ujs_point_evals_per_sec": n_points_global * steps_per_s,
+            "ujs_point_evals_per_sec": int(tr.x_batch_global.shape[0]) * steps_per_s,
             "pair_evals_per_sec": s_local * world * steps_per_s,
             "step_tflops_algorithmic": step_tf,
             "loss_first": loss_first, "loss_last": loss_last,
@@ -363,6 +374,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug-sized problem (not a valid bench number)")
+    ap.add_argument("--config", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE config; cfg5 is the headline workload, the others are informational")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
