@@ -309,6 +309,16 @@ def run_ours(args):
         step_flops += 3.0 * flops_per_pair(layer_sizes, e_.plan.jet.C) * e_.takes.s
     step_tf = step_flops * world / (ms_per_step * 1e-3) / 1e12
 
+    # ---- active-set change path: full rebuild of the update inputs on the device (inside tests, takes,
+    #      work list, window sums, affine jets) — what costs the reference an O(n m) index pass + an XLA recompile
+    rebuild_ms = None
+    if world == 1 and not args.skip_rebuild:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.set_active(np.ones(m, dtype=int))
+        torch.cuda.synchronize()
+        rebuild_ms = (time.perf_counter() - t0) * 1e3
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -333,7 +343,7 @@ def run_ours(args):
             "ujs_point_evals_per_sec": int(tr.x_batch_global.shape[0]) * steps_per_s,
             "pair_evals_per_sec": s_local * world * steps_per_s,
             "step_tflops_algorithmic": step_tf,
-            "loss_first": loss_first, "loss_last": loss_last,
+            "loss_first": loss_first, "loss_last": loss_last, "active_set_rebuild_ms": rebuild_ms,
             "clocks": clocks,
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": gpu_launches,
@@ -373,6 +383,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-rebuild", action="store_true")
     ap.add_argument("--small", action="store_true", help="debug-sized problem (not a valid bench number)")
     ap.add_argument("--config", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE config; cfg5 is the headline workload, the others are informational")

@@ -217,3 +217,37 @@ def test_activation_cache_matches_recompute(name):
     ev.forward(p2); ev.backward(ubar, p2, g1, accumulate=False)
     ev2.forward(p2); ev2.backward(ubar, p2, g2, accumulate=False)
     assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 2e-6
+
+
+def test_multilevel_decomposition_npou2_matches_oracle():
+    """MultilevelRectangularDecompositionND (two partitions of unity, fbpinns/decompositions.py:338-375): per-level
+    N/D quotient, sum over levels, /npou (fbpinns/trainers.py:163-170) — ujs, loss and gradients vs the oracle."""
+    import gpu_common
+    from fbpinns_b200 import decompositions
+    from fbpinns_b200.constants import get_subdomain_ws
+    xs1 = [np.linspace(-1, 1, 3), np.linspace(0, 1, 2)]
+    xs2 = [np.linspace(-1, 1, 5), np.linspace(0, 1, 4)]
+    c = configs.cfg3_burgers(n_sub=(3, 2), n_pts=(40, 30), line_scheduler=False)
+    c.decomposition = decompositions.MultilevelRectangularDecompositionND
+    c.decomposition_init_kwargs = dict(subdomain_xss=[xs1, xs2],
+                                       subdomain_wss=[get_subdomain_ws(xs1, 2.9), get_subdomain_ws(xs2, 2.9)], unnorm=(0., 3.))
+    k = common.make_case(c, seed=7, multilevel=True)
+    assert k.ui["takess"][0][4] == 2
+    for kernel in ["generic", "auto"]:
+        dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+        ev = inp.evaluators[0]
+        assert ev.takes.npou == 2 and ev.takes.q > ev.takes.n
+        ujets = ev.forward(params)
+        ref = common.oracle_ujs(k, 0, torch.float64, constrained=False)
+        for (iu, p), got, r in zip(ev.plan.jet.required_ujs, gpu_common.ujets_columns(ev.plan.jet, ujets), ref):
+            assert common.rel_err(got, r[:, 0]) < TOL, (kernel, p)
+        step, adam, _ = _make_step(k, inp, params, params.device)
+        assert step.affine[0] is None            # npou > 1: constraining goes through the generic path
+        step.grads.zero_()
+        loss = step.forward_loss()
+        loss.backward()
+        ref_loss, g_layers, _ = common.oracle_loss_and_grads(k, torch.float64)
+        assert abs(loss.item() - ref_loss) <= TOL * abs(ref_loss)
+        got = unpack_params(ev.plan, step.grads[:len(inp.active_ims)].contiguous())
+        for (gw, gb), (rw, rb) in zip(got, g_layers):
+            assert common.rel_err(gw.cpu().numpy(), rw) < TOL and common.rel_err(gb.cpu().numpy(), rb) < TOL
