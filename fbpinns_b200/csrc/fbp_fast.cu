@@ -97,7 +97,10 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
                       const float* d_cache, cudaStream_t stream) {
     if (tv->m_active == 0) return 0;
     FBP_REQUIRE(d_gpart != nullptr || tv->n_items_active == 0, "fbp_backward(tiled): null workspace");
-    if (tv->n_items_active > 0) {
+    const bool run_kernels = !(accumulate & FBP_BWD_REDUCE_ONLY);
+    const bool run_reduce = !(accumulate & FBP_BWD_NO_REDUCE);
+    accumulate &= FBP_BWD_ACCUMULATE;
+    if (run_kernels && tv->n_items_active > 0) {
         FastArgs a;
         fill_args(plan, tv, d_x, d_params, d_sub_static, a);
         a.grow = d_grow;
@@ -106,6 +109,7 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
         a.order = tv->d_item_order_bwd;
         if (int rc = dispatch(plan, true, a, tv->n_items_active, stream)) return rc;
     }
+    if (!run_reduce) return 0;
     const int64_t total = (int64_t)tv->m_active * plan->dev.P;
     fast_grad_reduce_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(d_gpart, tv->d_sub_item_off, tv->m_active,
                                                                             plan->dev.P, d_grads, accumulate);

@@ -83,8 +83,39 @@ class HaloExchange:
         self.recv_idx = tl(np.concatenate([halo["recv"][j] for j in range(w) if j != r]) if w > 1 else [])
         self.active = (sum(self.send_counts) + sum(self.recv_counts)) > 0
 
-    def _a2a(self, out, inp, out_splits, in_splits):
-        dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=self.shard.group)
+    def _a2a(self, out, inp, out_splits, in_splits, async_op=False):
+        return dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits,
+                                      group=self.shard.group, async_op=async_op)
+
+    # split-phase variants: start() enqueues the exchange on NCCL's stream and returns immediately, so kernels launched
+    # afterwards on the compute stream overlap it; finish() makes the compute stream wait and applies the result
+    def forward_start(self, rows):
+        inp = rows.index_select(0, self.send_idx).contiguous()
+        out = torch.empty((int(self.recv_idx.numel()), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        work = self._a2a(out, inp, list(self.recv_counts), list(self.send_counts), async_op=True)
+        return work, inp, out
+
+    def forward_finish(self, rows, pending):
+        work, _, out = pending
+        work.wait()
+        off = 0
+        for c in self.recv_counts:
+            if c:
+                rows.index_add_(0, self.recv_idx[off:off + c], out[off:off + c])
+                off += c
+        return rows
+
+    def backward_start(self, rows):
+        inp = rows.index_select(0, self.recv_idx).contiguous()
+        out = torch.empty((int(self.send_idx.numel()), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        work = self._a2a(out, inp, list(self.send_counts), list(self.recv_counts), async_op=True)
+        return work, inp, out
+
+    def backward_finish(self, rows, pending):
+        work, _, out = pending
+        work.wait()
+        rows.index_copy_(0, self.send_idx, out)
+        return rows
 
     def forward_add(self, rows):
         "rows (q, V): adds into owned shared rows the partial sums the other ranks computed for them (in rank order)"
@@ -126,15 +157,64 @@ class ShardedEvaluator:
         self.nsum = torch.empty((max(t.q, 1), ev.V), dtype=torch.float32, device=dev)[:t.q]
         # denominators: local partial -> total on the owners (once per active-set change)
         self.halo.forward_add(ev.dsum[:t.q])          # collective: every rank calls it, even with no rows
+        self._split_work_list()
+
+    def _split_work_list(self):
+        """Boundary work items = items of subdomains that hold at least one row shared with another rank.  They are
+        launched first in the forward pass (their row sums feed the halo exchange, which then overlaps the interior
+        items) and last in the reverse pass (they need the cotangents that come back).  Tiled plans only."""
+        ev, t = self.ev, self.ev.takes
+        self.overlap = bool(ev.plan.is_fast) and t.s > 0 and self.shard.world > 1
+        if not self.overlap:
+            return
+        dev = ev.x.device
+        halo_row = torch.zeros(max(t.q, 1), dtype=torch.bool, device=dev)
+        halo_row[self.halo.send_idx] = True
+        halo_row[self.halo.recv_idx] = True
+        bsub = torch.zeros(t.m_all, dtype=torch.bool, device=dev)
+        bsub[t.spair_sub.long()[halo_row[t.spair_row.long()]]] = True
+        bsub = bsub.cpu().numpy()
+        items = t.items_host
+        is_b = bsub[items[:, 0]]
+        of, ob = t.item_order_fwd.cpu().numpy(), t.item_order_bwd.cpu().numpy()
+        mk = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), dtype=torch.int32, device=dev)
+        self._orders = [mk(of[is_b[of]]), mk(of[~is_b[of]]), mk(ob[~is_b[ob]]), mk(ob[is_b[ob]])]
+        base = t.view()
+
+        def view(order, fwd):
+            v = type(base).from_buffer_copy(base)
+            if fwd:
+                v.d_item_order_fwd, v.n_items = (order.data_ptr() if order.numel() else None), int(order.numel())
+            else:
+                v.d_item_order_bwd, v.n_items_active = (order.data_ptr() if order.numel() else None), int(order.numel())
+            return v
+        self.v_fwd_boundary, self.v_fwd_interior = view(self._orders[0], True), view(self._orders[1], True)
+        self.v_bwd_interior, self.v_bwd_boundary = view(self._orders[2], False), view(self._orders[3], False)
 
     def forward(self, params):
         lib = _lib.load()
         ev = self.ev
         tv = ev.takes.view()
-        check(lib.fbp_forward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
-                              ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, ptr(ev.cache), stream_ptr()), "fbp_forward")
-        check(lib.fbp_row_sums(ev.plan.handle, C.byref(tv), ptr(ev.pair_out), ptr(self.nsum), stream_ptr()), "fbp_row_sums")
-        self.halo.forward_add(self.nsum)
+
+        def fwd(view):
+            check(lib.fbp_forward(ev.plan.handle, C.byref(view), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
+                                  ptr(ev.pair_out), ptr(ev.scratch), ev.scratch_floats, ptr(ev.cache), stream_ptr()),
+                  "fbp_forward")
+
+        def row_sums():
+            check(lib.fbp_row_sums(ev.plan.handle, C.byref(tv), ptr(ev.pair_out), ptr(self.nsum), stream_ptr()),
+                  "fbp_row_sums")
+        if self.overlap:
+            fwd(self.v_fwd_boundary)                      # subdomains touching the slab interfaces first
+            row_sums()                                    # shared rows are complete now (interior rows are not: unused)
+            pending = self.halo.forward_start(self.nsum)  # exchange runs on NCCL's stream ...
+            fwd(self.v_fwd_interior)                      # ... while the interior subdomains are evaluated
+            row_sums()
+            self.halo.forward_finish(self.nsum, pending)
+        else:
+            fwd(tv)
+            row_sums()
+            self.halo.forward_add(self.nsum)
         ujets = torch.empty((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
         check(lib.fbp_reduce_rows_forward(ev.plan.handle, C.byref(tv), ptr(self.nsum), ptr(ev.dsum), ptr(ev.affine),
                                           ptr(ujets), stream_ptr()), "fbp_reduce_rows_forward")
@@ -148,10 +228,20 @@ class ShardedEvaluator:
         ub.index_copy_(0, self.owned_idx, ujets_bar_owned.contiguous().float())
         check(lib.fbp_reduce_backward(ev.plan.handle, C.byref(tv), ptr(ub), ptr(ev.dsum), ptr(ev.affine), ptr(ev.grow),
                                       stream_ptr()), "fbp_reduce_backward")
-        self.halo.backward_return(ev.grow[:ev.takes.q])
-        check(lib.fbp_backward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
-                               ptr(ev.grow), ptr(grads), 1, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats,
-                               ptr(ev.cache), stream_ptr()), "fbp_backward")
+        def bwd(view, flags):
+            check(lib.fbp_backward(ev.plan.handle, C.byref(view), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
+                                   ptr(ev.grow), ptr(grads), flags, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats,
+                                   ptr(ev.cache), stream_ptr()), "fbp_backward")
+        rows = ev.grow[:ev.takes.q]
+        if self.overlap:
+            pending = self.halo.backward_start(rows)      # owners' cotangents of the shared rows travel back ...
+            bwd(self.v_bwd_interior, 2)                   # ... while the interior subdomains run (kernels only)
+            self.halo.backward_finish(rows, pending)
+            bwd(self.v_bwd_boundary, 2)
+            bwd(tv, 4 | 1)                                # sum every item's partial gradients, add into grads
+        else:
+            self.halo.backward_return(rows)
+            bwd(tv, 1)
 
 
 class _ShardedSum(torch.autograd.Function):
@@ -267,17 +357,20 @@ def make_sharded_update(base_cls):
             self.grads.zero_()
             self.hook.grad = None
             loss = self.forward_loss()
-            loss.backward()
             w0 = self.inp.weights[0]
+            with torch.no_grad():
+                # the global loss is only reported: reduce it asynchronously, hidden behind the reverse kernels
+                gl = (loss.detach() * w0).reshape(1)
+                pending = dist.all_reduce(gl, group=self.shard.group, async_op=True)
+            loss.backward()
             pg = self.problem_grad()
             with torch.no_grad():
                 if pg is not None:
                     pg = (pg * w0).contiguous()
                     dist.all_reduce(pg, group=self.shard.group)
-                gl = (loss.detach() * w0).reshape(1)
-                dist.all_reduce(gl, group=self.shard.group)
                 self.adam.step(self.params, self.grads, self.active_ims_dev,
                                self.prob_flat if pg is not None else None, pg)
+                pending.wait()
                 self.loss_out.copy_(gl[0])
             return self.loss_out
 

@@ -230,9 +230,19 @@ class Poisson2D(Problem):
         return {"dims": (1, 2), "a": a, "b": b, "sd": sd}, {}
 
     @staticmethod
+    def source(all_params, x_batch):
+        "f of -(u_xx + u_yy) = f for the manufactured solution"
+        a, b = all_params["static"]["problem"]["a"], all_params["static"]["problem"]["b"]
+        x, y = x_batch[:, 0:1], x_batch[:, 1:2]
+        return (a * a + b * b) * math.pi ** 2 * torch.sin(a * math.pi * x) * torch.sin(b * math.pi * y)
+
+    @staticmethod
     def sample_constraints(all_params, domain, key, sampler, batch_shapes):
+        # the source term is a constraining value carried with the points (like u_boundary / u_data of the reference
+        # problems, fbpinns/problems.py:106-113, 250-256): static, so it is not recomputed every step
         x_batch_phys = domain.sample_interior(all_params, key, sampler, batch_shapes[0])
-        return [[x_batch_phys, ((0, (0, 0)), (0, (1, 1)))], ]
+        f_phys = Poisson2D.source(all_params, x_batch_phys)
+        return [[x_batch_phys, f_phys, ((0, (0, 0)), (0, (1, 1)))], ]
 
     @staticmethod
     def constraining_fn(all_params, x_batch, u):
@@ -243,10 +253,7 @@ class Poisson2D(Problem):
 
     @staticmethod
     def loss_fn(all_params, constraints):
-        a, b = all_params["static"]["problem"]["a"], all_params["static"]["problem"]["b"]
-        x_batch, uxx, uyy = constraints[0]
-        x, y = x_batch[:, 0:1], x_batch[:, 1:2]
-        f = (a * a + b * b) * math.pi ** 2 * torch.sin(a * math.pi * x) * torch.sin(b * math.pi * y)
+        x_batch, f, uxx, uyy = constraints[0]
         return torch.mean((uxx + uyy + f) ** 2)
 
     @staticmethod

@@ -50,6 +50,10 @@ extern "C" {
 #define FBP_MAX_UD 4
 #define FBP_MAX_COMP 10     /* 1 + xd + xd*(xd+1)/2 at xd = 3 */
 
+#define FBP_BWD_ACCUMULATE 1
+#define FBP_BWD_NO_REDUCE 2
+#define FBP_BWD_REDUCE_ONLY 4
+
 #define FBP_ACT_TANH 0      /* FCN, fbpinns/networks.py:61-68 */
 #define FBP_WINDOW_COSINE 0 /* windows.cosine, fbpinns/windows.py:25-35 */
 
@@ -188,6 +192,10 @@ int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const fl
 
 /* Reverse pass through the pairs of the ACTIVE subdomains: d_grads [m_active][P] (overwritten when
  * accumulate == 0, added to otherwise — several constraints share one gradient buffer).
+ * `accumulate` is a bit set: 1 = add into d_grads; FBP_BWD_NO_REDUCE (2) = run the pair kernels of the view's work
+ * list only (per-item partials stay in d_gpart); FBP_BWD_REDUCE_ONLY (4) = only sum the partials into d_grads.
+ * The split lets a multi-GPU host run interior and boundary work items as separate launches around the halo
+ * exchange (tiled plans only).
  * d_gpart: workspace of fbp_backward_workspace_floats() floats (split-subdomain partial sums). */
 int64_t fbp_backward_workspace_floats(const fbp_plan* plan, const fbp_takes_view* tv);
 int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,

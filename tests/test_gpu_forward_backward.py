@@ -156,6 +156,7 @@ def test_partition_of_unity_property_full_size():
     k.offsets = np.array([0])
     k.jets = [JetSpec(cons[0][-1], 2, 1)]
     k.active = np.ones(k.m, dtype=int)
+    assert len(k.constraints_global[0]) == 2           # points + the static source term
     rng = np.random.default_rng(0)
     from oracle import ref_model
     k.layers = ref_model.init_fcn_params(rng, k.m, k.layer_sizes)
