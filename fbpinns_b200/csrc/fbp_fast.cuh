@@ -543,6 +543,17 @@ fast_backward_kernel(FastArgs a) {
         for (int kk = 0; kk < KK; ++kk) gacc[jj][kk] = make_float2(0.0f, 0.0f);
     }
 
+    // output-layer gradient partials live in registers for the whole work item (reduced once at the end):
+    // wlacc[j] = sum over this thread's points of sum_c rbar_c h_c[j] ; blacc = sum of rbar_0 (threads < TP)
+    float wlacc[TM];
+#pragma unroll
+    for (int j = 0; j < TM; ++j) wlacc[j] = 0.0f;
+    float blacc = 0.0f;
+    // first-layer gradients folded into the layer-0 tanh transpose when a thread's own activation slots can hold its
+    // partial sums (bias, 3 coordinates, NS slots) — otherwise the warp-row reduction below is used
+    constexpr int NQ0 = 4 + NS;
+    constexpr bool FOLD0 = (CF::NHID == 2) && (NQ0 <= 2 * C);
+
     for (int t0 = 0; t0 < count; t0 += TP) {
         const int cnt = min(TP, count - t0);
         // ---- S0: points, window jets, cotangent of the output jets ------------------------------------
@@ -577,6 +588,7 @@ fast_backward_kernel(FastArgs a) {
                 rb[c * TP + tid] = un_sd * (G[c] * w);
             }
             rb[tid] = un_sd * ub0;
+            blacc += un_sd * ub0;
         }
         __syncthreads();
 
@@ -613,24 +625,6 @@ fast_backward_kernel(FastArgs a) {
         }
         __syncthreads();
 
-        // ---- output layer gradients: rows k over warps, points over lanes -------------------------------
-        for (int k = warp; k < H; k += NW) {
-            float s = 0.0f;
-            for (int p = lane; p < TP; p += 32) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) s = fmaf(rb[c * TP + p], actL[k * RS + c * TP + p], s);
-            }
-            s = fbp_warp_sum(s);
-            if (lane == 0) gWL[k] += s;
-        }
-        if (warp == 0) {
-            float s = 0.0f;
-            for (int p = lane; p < TP; p += 32) s += rb[p];
-            s = fbp_warp_sum(s);
-            if (lane == 0) gBL[0] += s;
-        }
-        __syncthreads();
-
         // ---- tanh transpose of the last hidden layer, in place: actL <- abar ----------------------------
 #pragma unroll
         for (int j = 0; j < TM; ++j) {
@@ -644,6 +638,12 @@ fast_backward_kernel(FastArgs a) {
             float h0[C], h1[C], b0[C], b1[C], o0[C], o1[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) { h0[c] = hv[c].x; h1[c] = hv[c].y; b0[c] = wl * rv[c].x; b1[c] = wl * rv[c].y; }
+            {   // output-layer weight gradient: sum_c rbar_c * h_c for this thread's two points
+                float2 d = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int c = 0; c < C; ++c) d = ffma2(rv[c], hv[c], d);
+                wlacc[j] += d.x + d.y;
+            }
             fast_tanh_jets_bwd<CF>(h0, b0, o0);
             fast_tanh_jets_bwd<CF>(h1, b1, o1);
 #pragma unroll
@@ -692,7 +692,11 @@ fast_backward_kernel(FastArgs a) {
             fast_gemm<CF, TP, RS>(sm + CF::SM_WR1, act1, j0, p0, acc);
             __syncthreads();      // every read of act0 (G) and of act1 (G, D) is done
             prefetch_tile(t0 + TP);
-            // ---- tanh transpose of layer 0, in place: act0 <- abar0
+            // ---- tanh transpose of layer 0, in place: act0 <- abar0 (or, folded, this thread's partial sums of the
+            //      first-layer gradients over its two points, stored in its own activation slots)
+            const float2 zv0 = *reinterpret_cast<const float2*>(zs + p0);
+            const float2 zv1 = *reinterpret_cast<const float2*>(zs + TP + p0);
+            const float2 zv2 = *reinterpret_cast<const float2*>(zs + 2 * TP + p0);
 #pragma unroll
             for (int j = 0; j < TM; ++j) {
                 float2 hv[C];
@@ -703,14 +707,45 @@ fast_backward_kernel(FastArgs a) {
                 for (int c = 0; c < C; ++c) { h0[c] = hv[c].x; h1[c] = hv[c].y; }
                 fast_tanh_jets_bwd<CF>(h0, acc[j][0], o0);
                 fast_tanh_jets_bwd<CF>(h1, acc[j][1], o1);
+                if (FOLD0) {
+                    float q[NQ0 + 1];
+                    q[0] = o0[0] + o1[0];                                    // bias
+                    q[1] = fmaf(o0[0], zv0.x, o1[0] * zv0.y);                // coordinates
+                    q[2] = fmaf(o0[0], zv1.x, o1[0] * zv1.y);
+                    q[3] = fmaf(o0[0], zv2.x, o1[0] * zv2.y);
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    *reinterpret_cast<float2*>(act0 + (j0 + j) * RS + c * TP + p0) = make_float2(o0[c], o1[c]);
+                    for (int s = 0; s < NS; ++s) {
+                        const int c = s < NA2 ? 1 + 2 * s : 1 + 2 * NA2 + (s - NA2);
+                        q[4 + s] = o0[c] + o1[c];
+                    }
+                    // slot q of row j = element (component q/2, point p0 + q%2) of this thread's own block
+#pragma unroll
+                    for (int t = 0; t < NQ0; ++t) act0[(j0 + j) * RS + (t >> 1) * TP + p0 + (t & 1)] = q[t];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        *reinterpret_cast<float2*>(act0 + (j0 + j) * RS + c * TP + p0) = make_float2(o0[c], o1[c]);
+                }
             }
             __syncthreads();
+            if (FOLD0) {
+                // one thread per (unit j, quantity t): sum the partials of the TP/2 point pairs in fixed order
+                for (int o = tid; o < H * NQ0; o += NT) {
+                    const int j = o / NQ0, t = o - j * NQ0;
+                    const float* src = act0 + j * RS + (t >> 1) * TP + (t & 1);
+                    float v = 0.0f;
+#pragma unroll 8
+                    for (int pq = 0; pq < TP / 2; ++pq) v += src[2 * pq];
+                    if (t == 0) gB0[j] += v;
+                    else if (t < 4) gT[(t - 1) * H + j] += v;
+                    else gS[(t - 4) * H + j] += v;
+                }
+                __syncthreads();
+            }
         }
 
-        // ---- first-layer gradients: rows j over warps, points over lanes --------------------------------
+        // ---- first-layer gradients: rows j over warps, points over lanes (when not folded above) ---------
+        if (!FOLD0)
         for (int j = warp; j < H; j += NW) {
             float t0s = 0.0f, t1s = 0.0f, t2s = 0.0f, bs = 0.0f;
             float ssl[NS > 0 ? NS : 1];
@@ -736,6 +771,37 @@ fast_backward_kernel(FastArgs a) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) gS[s * H + j] += ssl[s];
             }
+        }
+        if (!FOLD0) __syncthreads();
+    }
+
+    // ---- output-layer gradients: reduce the per-thread partials over the threads of each unit group, fixed order
+    {
+        constexpr int GW = (TP / PPT) < 32 ? (TP / PPT) : 32;      // lanes of a warp that share a unit group
+        constexpr int NG = (TP / PPT) / GW;                        // such lane groups per unit group
+        float* red = zs;                                           // [JG*NG][TM] + [TP/32] scratch (zs/rb are free now)
+        static_assert(JG * NG * TM + 8 <= 3 * TP + C * TP, "reduction scratch does not fit");
+#pragma unroll
+        for (int j = 0; j < TM; ++j) {
+            float v = wlacc[j];
+#pragma unroll
+            for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid % GW) == 0) red[(tid / GW) * TM + j] = v;
+        }
+        float bv = fbp_warp_sum(blacc);                            // threads >= TP hold 0
+        if (lane == 0) red[JG * NG * TM + warp] = bv;
+        __syncthreads();
+        for (int k = tid; k < H; k += NT) {
+            const int g = k / TM, j = k - g * TM;
+            float v = 0.0f;
+#pragma unroll
+            for (int i = 0; i < NG; ++i) v += red[(g * NG + i) * TM + j];
+            gWL[k] += v;
+        }
+        if (tid == 0) {
+            float v = 0.0f;
+            for (int w = 0; w < NW; ++w) v += red[JG * NG * TM + w];
+            gBL[0] += v;
         }
         __syncthreads();
     }
