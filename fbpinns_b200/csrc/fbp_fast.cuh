@@ -346,15 +346,29 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
     const int j0 = jg * TM, p0 = pp * PPT;
 
     constexpr bool TMA_SAVE = (CF::NHID == 2) && (CF::TPF == CF::TPB);   // forward tile == reverse tile: bulk stores
+    // software prefetch of the next tile's points (pair -> point index -> coordinates: two dependent global loads)
+    int pf_pt = 0;
+    float pf_x[3] = {0.0f, 0.0f, 0.0f};
+    auto load_idx = [&](int t0n) {
+        if (tid < TP && t0n < count) pf_pt = a.spair_point[first + t0n + (tid < min(TP, count - t0n) ? tid : 0)];
+    };
+    auto load_val = [&](int t0n) {
+        if (tid < TP && t0n < count) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
+        }
+    };
+    load_idx(0);
+    load_val(0);
     for (int t0 = 0; t0 < count; t0 += TP) {
         const int cnt = min(TP, count - t0);
         if (TMA_SAVE && tid == 0) tma_store_wait_read();     // previous tile's bulk stores have read `act`
         if (tid < TP) {
-            const int pt = a.spair_point[first + t0 + (tid < cnt ? tid : 0)];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) zs[d * TP + tid] = d < xd ? (a.x[(int64_t)pt * xd + d] - mu[d]) * isd[d] : 0.0f;
+            for (int d = 0; d < 3; ++d) zs[d * TP + tid] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
         }
         __syncthreads();
+        load_idx(t0 + TP);
 
         float acc[TM][PPT][C];
         fast_layer0<CF, TP>(sm, zs, j0, p0, acc);
@@ -398,6 +412,7 @@ __global__ void __launch_bounds__(CF::NTF, CF::FWD_MINB) fast_forward_kernel(Fas
                 }
             }
         }
+        load_val(t0 + TP);
         // output layer (ud = 1): partial dot over this thread's TM units, reduced over the JG groups below
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -554,25 +569,49 @@ fast_backward_kernel(FastArgs a) {
     constexpr int NQ0 = 4 + NS;
     constexpr bool FOLD0 = (CF::NHID == 2) && (NQ0 <= 2 * C);
 
+    // software prefetch of the next tile's per-point inputs (two dependent global loads: pair -> point/row index ->
+    // coordinates / row cotangent): indices are requested at the start of the long GEMM phases, values after them,
+    // and both are consumed at the next tile's S0, so their latency never sits on the critical path
+    int pf_pt = 0, pf_row = 0;
+    float pf_x[3] = {0.0f, 0.0f, 0.0f}, pf_g[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) pf_g[c] = 0.0f;
+    auto load_idx = [&](int t0n) {
+        if (tid < TP && t0n < count) {
+            const int cn = min(TP, count - t0n);
+            const int pi = first + t0n + (tid < cn ? tid : 0);
+            pf_pt = a.spair_point[pi];
+            pf_row = a.spair_row[pi];
+        }
+    };
+    auto load_val = [&](int t0n) {
+        if (tid < TP && t0n < count) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
+            const float* gr = a.grow + (int64_t)pf_row * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) pf_g[c] = gr[a.ext[c]];
+        }
+    };
+    load_idx(0);
+    load_val(0);
+
     for (int t0 = 0; t0 < count; t0 += TP) {
         const int cnt = min(TP, count - t0);
         // ---- S0: points, window jets, cotangent of the output jets ------------------------------------
         if (tid < TP) {
             const bool valid = tid < cnt;
-            const int pi = first + t0 + (valid ? tid : 0);
-            const int pt = a.spair_point[pi];
             float z[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                z[d] = d < xd ? (a.x[(int64_t)pt * xd + d] - mu[d]) * isd[d] : 0.0f;
+                z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
                 zs[d * TP + tid] = z[d];
             }
             float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
             fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
-            const float* gr = a.grow + (int64_t)a.spair_row[pi] * C;
             float G[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) G[c] = valid ? gr[a.ext[c]] : 0.0f;
+            for (int c = 0; c < C; ++c) G[c] = valid ? pf_g[c] : 0.0f;
             float ub0 = G[0] * w;
 #pragma unroll
             for (int s = 0; s < NA2; ++s) {
@@ -591,6 +630,7 @@ fast_backward_kernel(FastArgs a) {
             blacc += un_sd * ub0;
         }
         __syncthreads();
+        load_idx(t0 + TP);
 
         // ---- forward recompute -------------------------------------------------------------------------
         float acc[TM][PPT][C];
@@ -651,6 +691,7 @@ fast_backward_kernel(FastArgs a) {
                 *reinterpret_cast<float2*>(actL + (j0 + j) * RS + c * TP + p0) = make_float2(o0[c], o1[c]);
         }
         __syncthreads();
+        if (CF::NHID == 1) load_val(t0 + TP);
 
         if (CF::NHID == 2) {
             // ---- G: Wbar1[j][k] += sum_{c,p} abar1[j][c][p] * h0[k][c][p] ; bbar1[j] += sum_p abar1[j][0][p]
@@ -665,15 +706,25 @@ fast_backward_kernel(FastArgs a) {
                         for (int jj = 0; jj < JJ; ++jj) av[jj] = *reinterpret_cast<const float4*>(ab + (4 * jj) * RS + c * TP + pq);
 #pragma unroll
                         for (int kk = 0; kk < KK; ++kk) hv[kk] = *reinterpret_cast<const float4*>(hp + (8 * kk) * RS + c * TP + pq);
+#if FBP_G_FFMA2
+                        // two passes (points 0-1, then 2-3) so that the two updates of one accumulator are JJ*KK
+                        // instructions apart instead of back to back
+#pragma unroll
+                        for (int jj = 0; jj < JJ; ++jj)
+#pragma unroll
+                            for (int kk = 0; kk < KK; ++kk)
+                                gacc[jj][kk] = ffma2(make_float2(av[jj].x, av[jj].y), make_float2(hv[kk].x, hv[kk].y), gacc[jj][kk]);
+#pragma unroll
+                        for (int jj = 0; jj < JJ; ++jj)
+#pragma unroll
+                            for (int kk = 0; kk < KK; ++kk)
+                                gacc[jj][kk] = ffma2(make_float2(av[jj].z, av[jj].w), make_float2(hv[kk].z, hv[kk].w), gacc[jj][kk]);
+#endif
 #pragma unroll
                         for (int jj = 0; jj < JJ; ++jj) {
 #pragma unroll
                             for (int kk = 0; kk < KK; ++kk) {
 #if FBP_G_FFMA2
-                                float2 g = gacc[jj][kk];
-                                g = ffma2(make_float2(av[jj].x, av[jj].y), make_float2(hv[kk].x, hv[kk].y), g);
-                                g = ffma2(make_float2(av[jj].z, av[jj].w), make_float2(hv[kk].z, hv[kk].w), g);
-                                gacc[jj][kk] = g;
 #else
                                 float g = gacc[jj][kk].x;
                                 g = fmaf(av[jj].x, hv[kk].x, g);
@@ -692,6 +743,7 @@ fast_backward_kernel(FastArgs a) {
             fast_gemm<CF, TP, RS>(sm + CF::SM_WR1, act1, j0, p0, acc);
             __syncthreads();      // every read of act0 (G) and of act1 (G, D) is done
             prefetch_tile(t0 + TP);
+            load_val(t0 + TP);
             // ---- tanh transpose of layer 0, in place: act0 <- abar0 (or, folded, this thread's partial sums of the
             //      first-layer gradients over its two points, stored in its own activation slots)
             const float2 zv0 = *reinterpret_cast<const float2*>(zs + p0);
