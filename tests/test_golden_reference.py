@@ -141,3 +141,25 @@ def test_cuda_path_matches_reference_golden(name, kernel):
     assert common.rel_err(vev.dsum[:takes.q, 0].cpu().numpy(), g["wp"][:, 0]) < 1e-5
     us = vev.pair_values_reference_order()[:, 0].cpu().numpy()
     assert common.rel_err(us, g["us"][:, 0]) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_inference_api_matches_reference_golden(name):
+    "analysis.FBPINN_model / FBPINN_solution (value-only twin of the hot path) on the reference-generated fixtures"
+    from fbpinns_b200 import analysis, networks, domains
+    from fbpinns_b200.constants import Constants
+    g, cs, layers = _load(name)
+    prob = getattr(problems, cs["problem"])
+    sd, _ = decompositions.RectangularDecompositionND.init_params(**cs["dkw"])
+    sp, tp = prob.init_params(**cs["pkw"])
+    c = Constants(problem=prob, problem_init_kwargs=cs["pkw"], decomposition=decompositions.RectangularDecompositionND,
+                  decomposition_init_kwargs=cs["dkw"], network=networks.FCN,
+                  network_init_kwargs=dict(layer_sizes=cs["layer_sizes"]))
+    all_params = {"static": {"problem": sp, "decomposition": sd},
+                  "trainable": {"network": {"subdomain": {"layers": [(torch.as_tensor(w), torch.as_tensor(b)) for w, b in layers]}}}}
+    u, wp, us = analysis.FBPINN_model(c, all_params, g["active_in"], torch.as_tensor(cs["x"]))
+    assert common.rel_err(u.cpu().numpy(), g["u"]) < 1e-5
+    assert common.rel_err(wp.cpu().numpy(), g["wp"]) < 1e-5
+    assert common.rel_err(us.cpu().numpy(), g["us"]) < 1e-5
+    assert torch.equal(analysis.FBPINN_solution(c, all_params, g["active_in"], torch.as_tensor(cs["x"])), u)
