@@ -72,10 +72,13 @@ struct FastCfg {
     static constexpr int fwd_floats(int tp) {
         return SM_PARAMS + 3 * tp + (NHID == 2 ? H * C * tp : 0) + JG * C * tp + C * tp;
     }
-    static constexpr bool fwd_ok(int tp) { return fwd_floats(tp) * 4 <= 110 * 1024 && JG * (tp / PPT) <= 256; }
+#ifndef FBP_TPF_CAP
+#define FBP_TPF_CAP 64       // measured: 64-point tiles (more, smaller CTAs per SM) beat 128 (127.0 vs 116.4 steps/s)
+#endif
+    static constexpr bool fwd_ok(int tp) { return tp <= FBP_TPF_CAP && fwd_floats(tp) * 4 <= 110 * 1024 && JG * (tp / PPT) <= 256; }
     static constexpr int TPF = fwd_ok(128) ? 128 : (fwd_ok(64) ? 64 : 32);
     static constexpr int NTF = JG * (TPF / PPT);
-    static constexpr int FWD_MINB = fwd_ok(TPF) ? 2 : 1;
+    static constexpr int FWD_MINB = !fwd_ok(TPF) ? 1 : (fwd_floats(TPF) * 4 <= 56 * 1024 && NTF <= 128 ? 4 : 2);
 
     // backward tile
     static constexpr int SM_GRAD = 3 * H + H + (NS > 0 ? NS : 1) * H + (NHID == 2 ? H : 0) + H + 4;   // T, B0, S, B1, WL, BL
@@ -83,7 +86,7 @@ struct FastCfg {
         return SM_PARAMS + SM_GRAD + 3 * tp + C * tp + NHID * H * (C * tp + 4);
     }
 #ifndef FBP_TPB_CAP
-#define FBP_TPB_CAP 128
+#define FBP_TPB_CAP 64
 #endif
     static constexpr bool bwd_ok(int tp) { return tp <= FBP_TPB_CAP && bwd_floats(tp) * 4 <= 200 * 1024 && JG * (tp / PPT) <= 256; }
     static constexpr int TPB = bwd_ok(128) ? 128 : (bwd_ok(64) ? 64 : 32);
