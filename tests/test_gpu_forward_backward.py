@@ -252,3 +252,27 @@ def test_multilevel_decomposition_npou2_matches_oracle():
         got = unpack_params(ev.plan, step.grads[:len(inp.active_ims)].contiguous())
         for (gw, gb), (rw, rb) in zip(got, g_layers):
             assert common.rel_err(gw.cpu().numpy(), rw) < TOL and common.rel_err(gb.cpu().numpy(), rb) < TOL
+
+
+@pytest.mark.parametrize("name,small", [
+    ("cfg5", dict(n_sub=(4, 4), n_pts=(48, 48), layer_sizes=(2, 64, 64, 1))),      # sweep network of config 5
+    ("cfg4", dict(n_sub=(3, 3, 3), n_pts=(12, 12, 12), layer_sizes=(3, 64, 64, 1))),  # config 4's true layer sizes
+    ("cfg3", dict(n_sub=(4, 4), n_pts=(40, 40), layer_sizes=(2, 64, 1), line_scheduler=False)),
+])
+def test_width64_kernel_instances_match_oracle(name, small):
+    "H = 64 instances of the tiled family (32-point reverse tiles, 4 weight-gradient quadrants): loss and gradients"
+    import gpu_common
+    k = common.make_case(configs.CONFIGS[name](**small), seed=11)
+    dd, inp, params = gpu_common.device_case(k, kernel="auto")
+    assert all(ev.plan.is_fast for ev in inp.evaluators)
+    step, adam, _ = _make_step(k, inp, params, params.device)
+    step.grads.zero_()
+    loss = step.forward_loss()
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss, g_layers, _ = common.oracle_loss_and_grads(k, torch.float64)
+    assert abs(loss.item() - ref_loss) <= TOL * abs(ref_loss), (loss.item(), ref_loss)
+    got = unpack_params(inp.evaluators[0].plan, step.grads[:len(inp.active_ims)].contiguous())
+    for l, ((gw, gb), (rw, rb)) in enumerate(zip(got, g_layers)):
+        ew, eb = common.rel_err(gw.cpu().numpy(), rw), common.rel_err(gb.cpu().numpy(), rb)
+        assert ew < TOL and eb < TOL, f"{name} layer {l}: grad rel err W {ew:.2e} b {eb:.2e}"
