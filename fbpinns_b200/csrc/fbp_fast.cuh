@@ -1,26 +1,34 @@
 // Tiled ("fast") kernel family: the roofline kernels of the FBPINN subdomain evaluation on sm_100a.
 //
 // One CTA per work item = (subdomain, contiguous range of its pairs).  The subdomain's parameters are staged
-// once in shared memory (hidden matrix both transposed and raw), its points are streamed in tiles of TP with
-// coalesced loads, and every linear layer of the jet propagation is a register-tiled FP32 GEMM
+// once in shared memory (hidden matrix both transposed and raw), its points are streamed in tiles of TP (64) with
+// coalesced, software-prefetched loads, and every linear layer of the jet propagation is a register-tiled FP32 GEMM
 //      A[j][(c,p)] = sum_k W[j][k] * H[k][(c,p)]        j: output unit, c: jet component, p: point of the tile
-// where H lives in shared memory as [k][c][p] (p contiguous: lanes read consecutive points, conflict free) and
+// where H lives in shared memory as [k][c][p] (p contiguous: lanes read consecutive point pairs, conflict free) and
 // W^T as [k][j] (a warp reads ONE float4 -> broadcast).  Each thread owns TM=8 output units x PPT=2 points x C
-// components (16*C accumulators), so one k-step costs 2 LDS.128 + C LDS.64 for 16*C FFMA.  tanh jets are applied
-// to the accumulators in registers and written back IN PLACE (one activation buffer per hidden layer).
+// components; the two points form the lanes of Blackwell's packed FP32 FMA (fma.rn.f32x2 -> FFMA2) with the weight as
+// scalar-broadcast operand, so one k-step costs 2 LDS.128 + C LDS.64 for 8*C FFMA2.  tanh jets are applied to the
+// accumulators in registers and written back IN PLACE (one activation buffer per hidden layer).
 //
-// Reverse pass (same CTA shape): recompute the forward keeping h^l per hidden layer, then per layer
-//   G: Wbar[j][k] += sum_{c,p} abar[j][c][p] h[k][c][p]   lanes own an 8x4 (j,k) register tile, warps split the
-//      points, operands read as float4 along p (row stride padded by 4 floats -> the 4/8 distinct rows of a
-//      request fall in distinct banks), accumulators persist in registers across the tiles of the work item;
-//   D: hbar[k][(c,p)] = sum_j W[j][k] abar[j][(c,p)]      same shape as the forward GEMM with the raw matrix;
-//   tanh-jet transpose in registers, written over h^l.
-// First / last layers (K = xd <= 3, M = ud = 1) are not GEMM shaped: they are fused into the epilogues and their
-// gradients are warp-row reductions into shared-memory accumulators.
+// Forward: layer 0 (K = xd) -> [hidden GEMM -> tanh jets] -> output layer fused as a partial dot -> window jets and
+// Leibniz product per point -> coalesced store of the tile's [TP][C] block.  When an activation cache is given, the
+// last hidden layer's jets (the tile's [H][C][TP] shared-memory image) are saved with TMA bulk stores.
+//
+// Reverse (same CTA shape): h0 is recomputed (cheap), h1 is TMA-loaded from the activation cache into shared memory
+// (cp.async.bulk + mbarrier, issued one tile ahead) — or recomputed when no cache is given — then
+//   tanh-jet transpose of the last hidden layer in registers (+ the output-layer weight gradient as per-thread
+//     register partials, reduced once per work item),
+//   G: Wbar[j][k] += sum_{c,p} abar[j][c][p] h[k][c][p]   lanes own an 8x4 (j,k) tile of float2 accumulators (FFMA2
+//      over point pairs), warps split the points, operands read as float4 along p (row stride padded by 4 floats ->
+//      the 4/8 distinct rows of a request fall in distinct banks), accumulators persist across the tiles of the item,
+//   D: hbar[k][(c,p)] = sum_j W[j][k] abar[j][(c,p)]      same FFMA2 GEMM as the forward with the raw matrix,
+//   tanh-jet transpose of layer 0 (+ the first-layer gradients as per-thread partial sums written into the thread's
+//     own activation slots and summed by one thread per output, fixed order).
 // Results per work item go to gpart[item][P]; a second kernel sums the items of a subdomain in fixed order
 // (deterministic, no float atomics anywhere).
 //
 // Bound: FP32 FMA pipe (CUDA cores).  Algorithmic FLOPs per pair: SURVEY §8d (F_fwd = 2 MAC_0 + 2 C sum MAC_l).
+// Measured evidence and the history of these choices: DESIGN.md §4.1, profiles/r1*_*.
 #pragma once
 #include "fbp_common.cuh"
 
