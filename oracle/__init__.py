@@ -14,9 +14,10 @@ Pinning status (see DESIGN.md §"Oracle"):
   * the reference itself cannot be imported in this image (it needs jax + optax, neither is
     installed and there is no network);
   * the oracle is pinned against the reference's own source executed here under a numpy-backed
-    shim of the small `jax.numpy` subset it uses (`tests/golden/make_golden.py`): per-pair model
-    values, window, norm/unnorm, `get_jmaps`, `_get_level_params`, `get_inputs` index algebra and
-    the schedulers are the reference's code run verbatim; derivatives (ujs) and parameter gradients
+    shim of the small jax subset it uses (`tests/golden/make_golden.py`, `make_golden_shim.py`):
+    per-pair model values, window, norm/unnorm, `get_jmaps`, `_get_level_params`, the batched
+    `inside_points / inside_models`, `get_inputs`, `_get_x_batch`, `_get_update_inputs` and the
+    schedulers are the reference's code run verbatim; derivatives (ujs) and parameter gradients
     are pinned by central finite differences of those reference values in float64;
   * the only self-checking code in the reference (`fbpinns/decompositions_base.py:87-128`, pair
     ordering == row-major nonzero of the dense inside mask) is restated as a test;

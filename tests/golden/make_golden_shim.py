@@ -13,6 +13,10 @@ What this pins (bit-for-bit the reference's code paths, evaluated in float64 aft
     * FBPINN_model: norm_fn, FCN.network_fn, unnorm_fn, window_fn (windows.cosine), both segment sums, /wp, /npou,
       constraining_fn -> u, wp, us, ws, us_raw;  derivatives (ujs) by central finite differences of that u
     * Problem.loss_fn / constraining_fn of the reference problems
+    * refindex.npz: the reference's own batched inside_points_batch / inside_models_batch (lax.map / lax.scan code,
+      checked here against its dense specification for several batch sizes), RectangularDecompositionND.inside_points /
+      inside_models, and FBPINNTrainer._get_x_batch + _get_update_inputs (per-constraint split of the takes) for
+      several 0/1/2 active masks on a two-constraint setup
 The outputs are committed as tests/golden/refmodel_*.npz and checked by tests/test_golden_reference.py against the
 oracle (and through it the CUDA path).  Run:  python tests/golden/make_golden_shim.py
 """
@@ -192,7 +196,30 @@ def install_shim():
     jax.ops = types.ModuleType("jax.ops")
     jax.ops.segment_sum = segment_sum
     jax.random = _Stub("jax.random")
-    jax.lax = _Stub("jax.lax")
+    jax.lax = types.ModuleType("jax.lax")
+
+    def lax_map(f, xs):
+        n = len(xs[0]) if isinstance(xs, (tuple, list)) else len(xs)
+        outs = [f(tuple(_wrap(np.asarray(x[i])) for x in xs) if isinstance(xs, (tuple, list)) else _wrap(np.asarray(xs[i])))
+                for i in range(n)]
+        if isinstance(outs[0], tuple):
+            return tuple(np.stack([np.asarray(o[j]) for o in outs]).view(AtArray) for j in range(len(outs[0])))
+        return np.stack([np.asarray(o) for o in outs]).view(AtArray)
+
+    def lax_scan(f, init, xs):
+        carry = init
+        n = len(xs[0]) if isinstance(xs, (tuple, list)) else len(xs)
+        ys = []
+        for i in range(n):
+            xi = tuple(_wrap(np.asarray(x[i])) for x in xs) if isinstance(xs, (tuple, list)) else _wrap(np.asarray(xs[i]))
+            carry, y = f(carry, xi)
+            ys.append(y)
+        return carry, (None if ys and ys[0] is None else ys)
+
+    def lax_dynamic_slice(x, start, sizes):
+        idx = tuple(slice(int(s0), int(s0) + int(sz)) for s0, sz in zip(start, sizes))
+        return _wrap(np.asarray(x)[idx])
+    jax.lax.map, jax.lax.scan, jax.lax.dynamic_slice = lax_map, lax_scan, lax_dynamic_slice
     mods = {"jax": jax, "jax.numpy": jnp, "jax.nn": jax.nn, "jax.tree_util": jax.tree_util, "jax.ops": jax.ops,
             "jax.random": jax.random, "jax.lax": jax.lax}
     for name in ["optax", "matplotlib", "matplotlib.pyplot", "matplotlib.collections", "IPython", "IPython.display",
@@ -325,8 +352,84 @@ def run_case(ref, case, rng):
     return out
 
 
+def run_index_case(ref, rng):
+    """A2-A4 with the reference's OWN batched inside tests (decompositions_base.py lax.map / lax.scan code) and its
+    own FBPINNTrainer._get_update_inputs (per-constraint split of the takes), on HarmonicOscillator1D (two
+    constraints) and BurgersEquation2D with scheduler-like 0/1/2 active masks."""
+    T = ref.trainers
+    dcls = ref.decompositions.RectangularDecompositionND
+    base = importlib.import_module("fbpinns.decompositions_base")
+    sys.path.insert(0, HERE)
+    from cases import case_setup
+    out = {}
+    for tag, name in [("ho", "ho1d_hardbc"), ("bg", "burgers2d")]:
+        cs = case_setup(name)
+        dstat, _ = dcls.init_params(**cs["dkw"])
+        m = dstat["m"]
+        x = cs["x"]
+        all_params = {"static": {"decomposition": dstat, "problem": {"dims": (1, x.shape[1])}}, "trainable": {}}
+        # the reference's batched implementation for several batch sizes against its own dense specification
+        ps = {"params": dstat["subdomain"]["params"]}
+        dense = np.asarray(dcls._inside_rectangleND(ps, _wrap(x), np.arange(m)))
+        nt, mt = np.nonzero(dense)
+        for bs in [1, 7, len(x)]:
+            n_take, m_take, inside_ims = base.inside_points_batch(ps, _wrap(x), _wrap(np.arange(m)), bs, dcls._inside_rectangleND)
+            assert np.array_equal(np.asarray(n_take), nt) and np.array_equal(np.asarray(m_take), mt), (tag, bs)
+            sel = _wrap(np.arange(0, m, 2))
+            ips, d = base.inside_models_batch(ps, _wrap(x), sel, bs, dcls._inside_rectangleND)
+            assert np.array_equal(np.asarray(ips), np.nonzero(dense[:, ::2].any(1))[0]), (tag, bs)
+        n_take, m_take, inside_ims = dcls.inside_points(all_params, _wrap(x))
+        out[f"{tag}_x"], out[f"{tag}_n_take"], out[f"{tag}_m_take"] = x, np.asarray(n_take), np.asarray(m_take)
+        out[f"{tag}_inside_ims"] = np.asarray(inside_ims)
+        ips, d = dcls.inside_models(all_params, _wrap(x), _wrap(np.arange(1, m, 3)))
+        out[f"{tag}_models_sel"], out[f"{tag}_inside_ips"], out[f"{tag}_d"] = np.arange(1, m, 3), np.asarray(ips), np.array(float(d))
+
+    # _get_update_inputs on a two-constraint problem (physics grid + extra points), several active masks
+    cs = case_setup("burgers2d")
+    dstat, _ = dcls.init_params(**cs["dkw"])
+    m = dstat["m"]
+    x1 = cs["x"]
+    x2 = rng.uniform([-1, 0], [1, 1], size=(17, 2)).astype(np.float32)
+    v2 = rng.normal(size=(17, 1)).astype(np.float32)
+    constraints_global = [[_wrap(x1)], [_wrap(x2), _wrap(v2)]]
+    x_batch_global = _wrap(np.concatenate([x1, x2]))
+    offsets = _wrap(np.array([0, len(x1)]))
+    fs = np.zeros((len(x1) + len(x2), 2), dtype=bool)
+    fs[:len(x1), 0] = True
+    fs[len(x1):, 1] = True
+    trainable = {"network": {"subdomain": {"layers": [(_wrap(np.zeros((m, 2, 2), np.float32)), _wrap(np.zeros((m, 2), np.float32)))]}}}
+    all_params = {"static": {"decomposition": dstat, "problem": {"dims": (1, 2)}}, "trainable": trainable}
+    dummy = types.SimpleNamespace(c=types.SimpleNamespace(n_steps=1))
+    dummy._get_x_batch = lambda *a: T.FBPINNTrainer._get_x_batch(dummy, *a)
+    out["ui_x1"], out["ui_x2"], out["ui_v2"] = x1, x2, v2
+    masks = []
+    for trial in range(4):
+        active = rng.integers(0, 3, size=m)
+        active[rng.integers(0, m)] = 1
+        if trial == 0:
+            active[:] = 1
+        masks.append(active.copy())
+        (active2, merge_active, active_opt_states, active_params, fixed_params, static_params, takess, constraints, x_batch) = \
+            T.FBPINNTrainer._get_update_inputs(dummy, 0, active, all_params, trainable, x_batch_global, constraints_global,
+                                               _wrap(fs), offsets, dcls, None)
+        out[f"ui{trial}_active_in"], out[f"ui{trial}_active_out"] = active, np.asarray(active2)
+        out[f"ui{trial}_x_batch"] = np.asarray(x_batch)
+        out[f"ui{trial}_n_active_params"] = np.array(np.asarray(active_params["network"]["subdomain"]["layers"][0][0]).shape[0])
+        out[f"ui{trial}_n_fixed_params"] = np.array(np.asarray(fixed_params["network"]["subdomain"]["layers"][0][0]).shape[0])
+        for ic, tk in enumerate(takess):
+            for nm, a in zip(["m_take", "n_take", "p_take", "np_take"], tk[:4]):
+                out[f"ui{trial}_c{ic}_{nm}"] = np.asarray(a)
+            out[f"ui{trial}_c{ic}_npou"] = np.array(tk[4])
+            for j, c_ in enumerate(constraints[ic]):
+                out[f"ui{trial}_c{ic}_arr{j}"] = np.asarray(c_)
+    out["ui_trials"] = np.array(len(masks))
+    np.savez_compressed(os.path.join(HERE, "refindex.npz"), **out)
+    print("refindex.npz:", len(out), "arrays;", "pairs per trial:", [len(out[f"ui{t}_c0_m_take"]) for t in range(len(masks))])
+
+
 def main():
     ref = install_shim()
+    run_index_case(ref, np.random.default_rng(7))
     for i, name in enumerate(["ho1d_hardbc", "burgers2d", "wave3d"]):
         rng = np.random.default_rng(100 + i)
         case = make_case(ref, name, rng)

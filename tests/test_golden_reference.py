@@ -163,3 +163,76 @@ def test_inference_api_matches_reference_golden(name):
     assert common.rel_err(wp.cpu().numpy(), g["wp"]) < 1e-5
     assert common.rel_err(us.cpu().numpy(), g["us"]) < 1e-5
     assert torch.equal(analysis.FBPINN_solution(c, all_params, g["active_in"], torch.as_tensor(cs["x"])), u)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# refindex.npz: the reference's own batched inside tests and _get_update_inputs (rows A2-A4)
+
+def _index_golden():
+    return np.load(os.path.join(HERE, "golden", "refindex.npz"), allow_pickle=True)
+
+
+@pytest.mark.parametrize("tag,name", [("ho", "ho1d_hardbc"), ("bg", "burgers2d")])
+def test_oracle_inside_tests_match_reference(tag, name):
+    g = _index_golden()
+    cs = case_setup(name)
+    assert np.array_equal(g[f"{tag}_x"], cs["x"])
+    decomp = ref_takes.rectangular_init_params(**cs["dkw"])
+    n_take, m_take, ims = ref_takes.inside_points(decomp, cs["x"])
+    assert np.array_equal(n_take, g[f"{tag}_n_take"]) and np.array_equal(m_take, g[f"{tag}_m_take"])
+    assert np.array_equal(ims, g[f"{tag}_inside_ims"])
+    ips, d = ref_takes.inside_models(decomp, cs["x"], g[f"{tag}_models_sel"])
+    assert np.array_equal(ips, g[f"{tag}_inside_ips"])
+    assert abs(d - float(g[f"{tag}_d"])) <= 1e-6 * abs(float(g[f"{tag}_d"]))
+
+
+def _ui_inputs(g):
+    cs = case_setup("burgers2d")
+    x1, x2, v2 = g["ui_x1"], g["ui_x2"], g["ui_v2"]
+    assert np.array_equal(x1, cs["x"])
+    cons = [[x1], [x2, v2]]
+    xg = np.concatenate([x1, x2])
+    offsets, fs = ref_takes.constraint_tables([len(x1), len(x2)])
+    return cs, cons, xg, offsets, fs
+
+
+def test_oracle_update_inputs_match_reference():
+    "FBPINNTrainer._get_x_batch + _get_update_inputs of the reference vs the oracle, several 0/1/2 active masks"
+    g = _index_golden()
+    cs, cons, xg, offsets, fs = _ui_inputs(g)
+    decomp = ref_takes.rectangular_init_params(**cs["dkw"])
+    for t in range(int(g["ui_trials"])):
+        ui = ref_takes.get_update_inputs(g[f"ui{t}_active_in"], decomp, xg, cons, fs, offsets)
+        assert np.array_equal(ui["active"], g[f"ui{t}_active_out"])
+        assert np.array_equal(ui["x_batch"], g[f"ui{t}_x_batch"])
+        assert len(ui["active_ims"]) == int(g[f"ui{t}_n_active_params"]) and len(ui["fixed_ims"]) == int(g[f"ui{t}_n_fixed_params"])
+        for ic, tk in enumerate(ui["takess"]):
+            for got, nm in zip(tk[:4], ["m_take", "n_take", "p_take", "np_take"]):
+                assert np.array_equal(got, g[f"ui{t}_c{ic}_{nm}"]), (t, ic, nm)
+            assert tk[4] == int(g[f"ui{t}_c{ic}_npou"])
+            for j, arr in enumerate(ui["constraints"][ic]):
+                assert np.array_equal(arr, g[f"ui{t}_c{ic}_arr{j}"])
+
+
+@pytest.mark.gpu
+def test_device_update_inputs_match_reference():
+    "the CUDA index construction (fbp_inside_count / fbp_takes_*) vs the reference's own _get_update_inputs output"
+    from fbpinns_b200.engine import DeviceDecomposition
+    from fbpinns_b200.trainers import get_update_inputs
+    g = _index_golden()
+    cs, cons, xg, offsets, fs = _ui_inputs(g)
+    dev = torch.device("cuda:0")
+    sd, _ = decompositions.RectangularDecompositionND.init_params(**cs["dkw"])
+    dd = DeviceDecomposition(sd["subdomain"]["params"], sd["subdomain"]["pou"], dev)
+    cons_d = [[torch.as_tensor(a, device=dev) for a in con] for con in cons]
+    jets = [JetSpec(((0, ()), (0, (0,))), 2, 1), JetSpec(((0, ()),), 2, 1)]
+    for t in range(int(g["ui_trials"])):
+        inp = get_update_inputs(g[f"ui{t}_active_in"], None, dd, torch.as_tensor(xg, device=dev), cons_d, offsets, jets, [2, 16, 1])
+        assert np.array_equal(inp.active, g[f"ui{t}_active_out"])
+        assert np.array_equal(inp.x_batch.cpu().numpy(), g[f"ui{t}_x_batch"])
+        assert len(inp.active_ims) == int(g[f"ui{t}_n_active_params"]) and len(inp.fixed_ims) == int(g[f"ui{t}_n_fixed_params"])
+        for ic, tk in enumerate(inp.takess):
+            for got, nm in zip(tk.reference_arrays()[:4], ["m_take", "n_take", "p_take", "np_take"]):
+                assert np.array_equal(got, g[f"ui{t}_c{ic}_{nm}"]), (t, ic, nm)
+            for j, arr in enumerate(inp.constraints[ic]):
+                assert np.array_equal(arr.cpu().numpy(), g[f"ui{t}_c{ic}_arr{j}"])
