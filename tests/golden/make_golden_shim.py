@@ -343,6 +343,26 @@ def run_case(ref, case, rng):
         out["loss_on_fd_ujs"] = np.array(float(case["prob"].loss_fn(cut, cons)))
     except Exception as e:                     # problems with more than one constraint are exercised elsewhere
         out["loss_on_fd_ujs"] = np.array(np.nan)
+    # --- reverse mode: central finite differences over PARAMETERS of L0 = sum_p R_p u(x_p), u from the reference's
+    #     FBPINN_model (constrained), for a handful of parameter entries of every layer
+    R = rng.normal(size=np.asarray(u).shape)
+    out["grad_R"] = R
+    picks, fds = [], []
+    for l, (w, b) in enumerate(layers64):
+        for which, arr in (("w", w), ("b", b)):
+            for _ in range(3):
+                idx = tuple(int(rng.integers(0, d)) for d in arr.shape)
+                old = float(arr[idx])
+                hp = 1e-6 * max(1.0, abs(old))
+                vals = []
+                for sgn in (+1, -1):
+                    arr[idx] = old + sgn * hp
+                    cut_p = {"static": cut["static"], "trainable": cut_all(full["trainable"])}
+                    vals.append(float((R * np.asarray(T.FBPINN_model(cut_p, x64, takes, model_fns, verbose=False)[0])).sum()))
+                arr[idx] = old
+                picks.append((l, 0 if which == "w" else 1) + idx + (0,) * (3 - len(idx)))
+                fds.append((vals[0] - vals[1]) / (2 * hp))
+    out["grad_picks"], out["grad_fd"] = np.array(picks), np.array(fds)
     # inputs
     out["x"] = x32
     for l, (w, b) in enumerate(case["layers"]):

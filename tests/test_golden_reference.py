@@ -236,3 +236,24 @@ def test_device_update_inputs_match_reference():
                 assert np.array_equal(got, g[f"ui{t}_c{ic}_{nm}"]), (t, ic, nm)
             for j, arr in enumerate(inp.constraints[ic]):
                 assert np.array_equal(arr.cpu().numpy(), g[f"ui{t}_c{ic}_arr{j}"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_parameter_gradients_match_finite_differences_of_reference(name):
+    "reverse mode of the oracle vs central differences over parameters of L0 = sum R u, u from the reference's FBPINN_model"
+    g, cs, layers = _load(name)
+    dc, lc, takes, prob, ap, x, cf = _oracle_model(g, cs, layers)
+    all_ims = g["all_ims"]
+    full = [(torch.tensor(w, dtype=torch.float64, requires_grad=True), torch.tensor(b, dtype=torch.float64, requires_grad=True))
+            for w, b in layers]
+    ims = torch.as_tensor(all_ims, dtype=torch.long)
+    lc = [(w[ims], b[ims]) for w, b in full]
+    u = ref_model.fbpinn_model(dc, lc, x, takes, cf, ap)[0]
+    L0 = (torch.as_tensor(g["grad_R"]) * u).sum()
+    grads = torch.autograd.grad(L0, [t for wb in full for t in wb], allow_unused=True)
+    for pick, fd in zip(g["grad_picks"], g["grad_fd"]):
+        l, which = int(pick[0]), int(pick[1])
+        gt = grads[2 * l + which]
+        idx = tuple(int(v) for v in pick[2:2 + gt.dim()])
+        got = float(gt[idx]) if gt is not None else 0.0
+        assert abs(got - fd) <= 1e-6 * max(1.0, abs(fd)) + 1e-7 * float(np.abs(g["grad_fd"]).max()), (name, pick, got, fd)
