@@ -10,6 +10,7 @@ torch only owns the device buffers, the stream and the autograd tape that links 
 """
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -225,7 +226,8 @@ class DeviceTakes:
 
     def set_tiling(self, tile_points, target_items=None):
         if target_items is None:
-            target_items = 8 * device_info()["sm_count"]
+            # FBP_TARGET_ITEMS: tuning knob for A/B runs (work items the list should have at least, if possible)
+            target_items = int(os.environ.get("FBP_TARGET_ITEMS", 0)) or 8 * device_info()["sm_count"]
         items, sub_item_off, nia, order_fwd, order_bwd = build_work_items(self.sub_off_host, self.m_active, tile_points,
                                                                           target_items)
         dev = self.sub_ids.device
