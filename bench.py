@@ -337,7 +337,7 @@ def run_ours(args):
                        if not args.small else "SMALL cfg5 16x16 subdomains 256x256 grid (debug)",
                        "layers": list(layer_sizes), "subdomains": m, "points": n_points_global,
                        "pairs_this_rank": s_local, "parallelism": f"subdomain-slabs x{world}" if world > 1 else "single GPU",
-                       "cuda_graph": tr.update.graph is not None, "kernel_family": "tiled" if ev.plan.is_fast else "generic",
+                       "cuda_graph": tr.update.graph is not None, "kernel_family": ("tensor+tiled" if ev.plan.kernel == "tensor" else "tiled") if ev.plan.is_fast else "generic",
                        "l2": "per-step working set (pair jets 175 MB + indices 105 MB) exceeds the 126 MB L2; "
                              "per-kernel timings flush L2 with a 256 MB write between launches"},
             "ujs_point_evals_per_sec": int(tr.x_batch_global.shape[0]) * steps_per_s,
@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", default="2,32,32,1", help="FCN layer sizes (sweep: 2,32,1 / 2,64,64,1)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled", "tensor"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-rebuild", action="store_true")

@@ -56,6 +56,7 @@ SIGNATURES = {
     "fbp_plan_is_fast": (_I32, [_P]),
     "fbp_plan_tile_points": (_I32, [_P]),
     "fbp_plan_set_kernel": (C.c_int, [_P, _I32]),
+    "fbp_plan_has_tensor": (_I32, [_P]),
     "fbp_plan_scratch_per_pair": (_I64, [_P]),
     "fbp_plan_cache_per_pair": (_I64, [_P]),
     "fbp_pack_params": (C.c_int, [_P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _P]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "fbp_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I32, _F, _F, _F, _F, _F, _P]),
     "fbp_fma_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
     "fbp_ffma2_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
+    "fbp_tc_selftest": (C.c_int, [_P, _P, _P, _I32, _P]),
 }
 
 _lib = None

@@ -95,6 +95,7 @@ int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
         pd.i1[c] = f1; pd.i2[c] = f2;
     }
     p->fast_id = fbp_fast_lookup(d, &p->fast);
+    p->tc_ok = p->fast_id >= 0 && fbp_tc_supported(p->fast, p->dev.C) != 0;
     p->mode = 0;
     *out = p;
     return 0;
@@ -109,10 +110,15 @@ int64_t fbp_plan_param_count(const fbp_plan* plan) { return plan ? plan->dev.P :
 int32_t fbp_plan_is_fast(const fbp_plan* plan) { return plan && plan->fast_id >= 0 ? 1 : 0; }
 int32_t fbp_plan_tile_points(const fbp_plan* plan) { return (plan && plan->use_fast()) ? plan->fast.tile_points : 128; }
 
+int32_t fbp_plan_has_tensor(const fbp_plan* plan) { return plan && plan->fast_id >= 0 && plan->tc_ok ? 1 : 0; }
+
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
     FBP_REQUIRE(plan, "fbp_plan_set_kernel: null plan");
-    FBP_REQUIRE(mode >= 0 && mode <= 2, "fbp_plan_set_kernel: mode must be 0, 1 or 2");
+    FBP_REQUIRE(mode >= 0 && mode <= 3, "fbp_plan_set_kernel: mode must be 0, 1, 2 or 3");
     FBP_REQUIRE(mode != 2 || plan->fast_id >= 0, "fbp_plan_set_kernel: no tiled kernel instance for this plan");
+    FBP_REQUIRE(mode != 3 || (plan->fast_id >= 0 && plan->tc_ok),
+                "fbp_plan_set_kernel: no tensor (tcgen05) kernel instance for this plan (needs H = 32, two hidden layers, "
+                "at most 5 jet components)");
     plan->mode = mode;
     return 0;
 }

@@ -80,8 +80,10 @@ struct fbp_plan {
     PlanDev dev;
     int fast_id;          // -1: no tiled instance
     FastSpec fast;
-    int mode;             // 0 auto, 1 generic, 2 tiled
+    bool tc_ok;           // the tcgen05 ("tensor") family has an instance for this plan
+    int mode;             // 0 auto, 1 generic, 2 tiled, 3 tensor (tcgen05 forward; the rest of the step stays tiled)
     bool use_fast() const { return mode == 1 ? false : fast_id >= 0; }
+    bool use_tc() const { return mode == 3 && tc_ok; }
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -156,6 +158,8 @@ int fbp_generic_backward(const fbp_plan* plan, const fbp_takes_view* tv, const f
 
 // tiled family: returns -1 if no instance matches
 int fbp_fast_lookup(const fbp_plan_desc* desc, FastSpec* spec);
+// tensor (tcgen05) family: 1 if it has an instance for this tiled spec with C jet components
+int fbp_tc_supported(const FastSpec& f, int C);
 int fbp_fast_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                      const float* d_sub_static, float* d_pair_out, float* d_cache, cudaStream_t stream);
 int64_t fbp_fast_backward_workspace(const fbp_plan* plan, const fbp_takes_view* tv);

@@ -1,5 +1,5 @@
 // Tiled kernel family: plan matching, launch glue and the deterministic partial-gradient reduction.
-#include "fbp_fast.cuh"
+#include "fbp_tc.cuh"
 
 __global__ void fast_grad_reduce_kernel(const float* __restrict__ gpart, const int32_t* __restrict__ sub_item_off,
                                         int m_active, int P, float* __restrict__ grads, int accumulate) {
@@ -85,6 +85,7 @@ int fbp_fast_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float
     a.pair_out = d_pair_out;
     a.cache = d_cache;
     a.order = tv->d_item_order_fwd;
+    if (plan->use_tc()) return fbp_tc_forward_launch(plan->fast, a, tv->n_items, stream);
     return dispatch(plan, false, a, tv->n_items, stream);
 }
 

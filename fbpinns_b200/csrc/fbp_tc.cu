@@ -1,0 +1,122 @@
+// tcgen05 ("tensor") kernel family: instantiations, launch glue and the MMA self-test.
+#include "fbp_tc.cuh"
+
+using namespace fbptc;
+
+// -----------------------------------------------------------------------------------------------------------------
+// Self-test of the one MMA form the family uses (A from tensor memory written row-wise by its owner threads, B from a
+// no-swizzle K-major shared-memory descriptor, N = 16 halves, 3xTF32): out[128][32] = A[128][32] * W[32][32]^T.
+// `variant` lets a hardware session probe descriptor conventions without rebuilding:
+//   bit 0: swap LBO and SBO in the descriptor          bit 1: descriptor version field 0 instead of 1
+//   bit 2: single TF32 pass (hi*hi only; expected error ~1e-3, distinguishes "wrong layout" from "wrong split")
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                            float* __restrict__ out, int variant) {
+    __shared__ __align__(128) float bhi[H * H];
+    __shared__ __align__(128) float blo[H * H];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = warp_uniform(), g = tid >> 7, r = tid & 127, j0 = 16 * g;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr uint32_t COL_AHI = 0, COL_ALO = 32, COL_D = 64;
+
+    stage_b(bhi, blo, W, H, 1, tid);
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tf32_split(A[r * H + j0 + 8 * ch + e], hi[e], lo[e]);
+        tmem_st8(tbase + lane_base + COL_AHI + j0 + 8 * ch, hi);
+        tmem_st8(tbase + lane_base + COL_ALO + j0 + 8 * ch, lo);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
+        tc_fence_after();
+        const uint32_t lbo = (variant & 1) ? B_SBO : B_LBO, sbo = (variant & 1) ? B_LBO : B_SBO;
+        uint64_t dh = make_smem_desc(smem_u32(bhi), lbo, sbo), dl = make_smem_desc(smem_u32(blo), lbo, sbo);
+        if (variant & 2) { dh &= ~((uint64_t)3 << 46); dl &= ~((uint64_t)3 << 46); }
+        for (int nh = 0; nh < 2; ++nh) {
+            if (variant & 4) {
+                constexpr uint32_t idesc = make_idesc_tf32(128, 16);
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_tf32_ts(tbase + COL_D + nh * 16, tbase + COL_AHI + ks * 8,
+                                dh + (uint64_t)((nh * 2 * B_SBO) >> 4) + (uint64_t)((ks * 2 * B_LBO) >> 4), idesc, ks != 0);
+            } else {
+                issue_gemm_half(tbase + COL_D + nh * 16, tbase + COL_AHI, tbase + COL_ALO, dh, dl, nh);
+            }
+            mma_commit(&bar[nh]);
+        }
+    }
+    mbar_wait_or_trap(&bar[g], 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        uint32_t v[8];
+        tmem_ld8(tbase + lane_base + COL_D + j0 + 8 * ch, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[r * H + j0 + 8 * ch + e] = __uint_as_float(v[e]);
+    }
+    mbar_wait_or_trap(&bar[1], 0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);
+}
+
+extern "C" int fbp_tc_selftest(const float* d_a, const float* d_w, float* d_out, int32_t variant, void* stream) {
+    FBP_REQUIRE(d_a && d_w && d_out, "fbp_tc_selftest: null buffer");
+    tc_selftest_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(d_a, d_w, d_out, variant);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// plan matching and launchers
+// -----------------------------------------------------------------------------------------------------------------
+int fbp_tc_supported(const FastSpec& f, int C) {
+    if (f.H != 32 || f.nhid != 2) return 0;
+    if (3 * C * 32 > (int)TMEM_COLS) return 0;
+    const int key = f.na2 * 4 + f.na1;
+    return key == 0 || key == 1 || key == 4 || key == 5 || key == 8;
+}
+
+template <class CF>
+static int tc_forward_one(const FastArgs& a, int grid, cudaStream_t st) {
+    constexpr size_t bytes = sizeof(float) * FwdSmem<CF>::FLOATS;
+    static bool configured = false;
+    if (!configured) {
+        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = true;
+    }
+    tc_forward_kernel<CF><<<grid, NT, bytes, st>>>(a);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+int fbp_tc_forward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st) {
+    switch (f.na2 * 4 + f.na1) {
+        case 0: return tc_forward_one<FastCfg<32, 2, 0, 0>>(a, grid, st);
+        case 1: return tc_forward_one<FastCfg<32, 2, 0, 1>>(a, grid, st);
+        case 4: return tc_forward_one<FastCfg<32, 2, 1, 0>>(a, grid, st);
+        case 5: return tc_forward_one<FastCfg<32, 2, 1, 1>>(a, grid, st);
+        case 8: return tc_forward_one<FastCfg<32, 2, 2, 0>>(a, grid, st);
+        default: break;
+    }
+    fbp_set_error("fbp_tc: no tensor-family instance for jets=(%d,%d)", f.na2, f.na1);
+    return 3;
+}

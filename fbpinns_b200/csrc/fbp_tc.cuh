@@ -1,0 +1,406 @@
+// tcgen05 ("tensor") kernel family: the hidden-layer GEMMs of the jet propagation on the 5th-generation tensor cores
+// of sm_100a, at FP32-equivalent accuracy through the 3xTF32 split (x = hi + lo, x*w ~ lo*w_hi + hi*w_lo + hi*w_hi,
+// every part rounded to TF32, FP32 accumulation in tensor memory).
+//
+// Why: ncu on the FFMA2 kernels (profiles/r1e_*) shows the FP32 FMA pipe as the binding resource of the GEMM phases;
+// the north star allows tensor-core MMA on the hidden layers in exactly that case, provided the tolerance holds.
+//
+// Shape of the mapping (plans with H = 32, two hidden layers, C <= 5 jet components):
+//   * tile = 128 pairs of one subdomain = the 128 lanes of tensor memory: ROW p of every operand is point p;
+//   * 256 threads: thread (g, p) owns point p and the 16 hidden units [16 g, 16 g + 16)  (g = warpgroup), so that
+//     warp w touches only the TMEM lanes 32 (w % 4) .. +31 it is allowed to;
+//   * A operands (activations, 128 x 32 per jet component) never touch shared memory: the thread that computed a row
+//     writes its hi and lo parts straight into tensor memory (tcgen05.st), and the MMAs read A from TMEM (".ts" form);
+//   * B operands (the subdomain's 32 x 32 matrix, hi and lo) are staged once per work item in shared memory in the
+//     canonical no-swizzle K-major core-matrix layout and addressed through UMMA shared-memory descriptors;
+//   * accumulators D[c] (128 x 32 per component) live in TMEM; one elected thread issues the MMAs
+//     (M = 128, N = 16, K = 8 per instruction; 12 per component and unit half) and commits them to an mbarrier per
+//     unit half, so warpgroup 0 starts its tanh-jet epilogue while the tensor core still works on the second half;
+//   * the epilogue reads the accumulators back row-wise (tcgen05.ld 32x32b: thread = point, registers = units), so
+//     the tanh jets, the output layer (a 32-long dot product per component) and the window/Leibniz product are all
+//     thread-local; the two unit halves meet once per tile through 5 floats per point in shared memory.
+//
+// TMEM column map (one allocation of 512 columns per CTA, hence one CTA per SM):
+//     [0, 32 C)  A hi   column c*32 + k          [32 C, 64 C)  A lo          [64 C, 96 C)  D   column c*32 + j
+//
+// Status: written and cross-compiled in round 1 after the GPU budget was spent; validated on hardware in round 2
+// (tests/test_gpu_tc.py, enabled with FBP_TC_TESTS=1).  The plan only uses this family when asked to
+// (fbp_plan_set_kernel(plan, 3)); the default stays the FFMA2 family.
+#pragma once
+#include "fbp_fast.cuh"
+
+namespace fbptc {
+
+constexpr int TP = 128;           // pairs per tile = TMEM lanes
+constexpr int NT = 256;           // threads: 2 warpgroups x 128 point rows
+constexpr int H = 32;
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---- UMMA descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp of CUTLASS, SmemDescriptor / InstrDescriptor) ------
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major: core matrices of 8 rows x 16 bytes (= 4 tf32) stored as 128
+// contiguous bytes; LBO = byte step between the two core matrices an MMA reads along K (K = 8 tf32), SBO = byte step
+// between groups of 8 rows.
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);            // [0,14)  start address >> 4
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;      // [16,30) leading byte offset >> 4
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;      // [32,46) stride byte offset >> 4
+    d |= (uint64_t)1 << 46;                                 // [46,48) descriptor version 1 (Blackwell)
+    // base offset [49,52) = 0, lbo mode [52] = 0, layout type [61,64) = 0 (SWIZZLE_NONE)
+    return d;
+}
+// instruction descriptor of tcgen05.mma.kind::tf32, FP32 accumulate, A and B K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4)                    // [4,6)   D format F32
+         | (2u << 7)                    // [7,10)  A format TF32
+         | (2u << 10)                   // [10,13) B format TF32
+         | (0u << 15) | (0u << 16)      // A, B K-major
+         | ((uint32_t)(N >> 3) << 17)   // [17,23) N >> 3
+         | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
+}
+
+// canonical K-major no-swizzle placement of element (row n, column k) of a [rows][32] tf32 matrix, in floats:
+// 8 x 4 core matrices of 32 floats, the 8 cores of a row group contiguous along K (LBO = 128 B), row groups 1024 B apart
+__host__ __device__ constexpr int bcore_index(int n, int k) { return ((n >> 3) * 8 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3); }
+constexpr uint32_t B_LBO = 128, B_SBO = 1024;
+
+// ---- TF32 split ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - __uint_as_float(hi));
+}
+
+// ---- tcgen05 wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {       // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {      // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; one thread issues for the CTA
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the mbarrier receives one arrival when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// warp index as a value the compiler knows to be warp-uniform, and the single-lane election used for MMA issue:
+// with both, ptxas keeps the MMA operands in uniform registers instead of wrapping every tcgen05.mma in a
+// waterfall loop (ELECT/PLOP3/BRA per instruction when the guard is `tid == 0`)
+__device__ __forceinline__ int warp_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// mbarrier wait that turns a lost arrival into a trap instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    long long t_start = 0;
+    for (int spin = 0;; ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (spin == 64) t_start = clock64();
+        if (spin > 64 && clock64() - t_start > 4000000000ll) __trap();      // ~2 s
+    }
+}
+
+// Stage a [32][32] matrix B[n][k] = src[n * sn + k * sk] (hi and lo TF32 parts) in the canonical layout.
+__device__ __forceinline__ void stage_b(float* bhi, float* blo, const float* __restrict__ src, int sn, int sk, int tid) {
+    for (int i = tid; i < H * H; i += NT) {
+        const int n = i >> 5, k = i & 31;
+        uint32_t hi, lo;
+        tf32_split(src[n * sn + k * sk], hi, lo);
+        bhi[bcore_index(n, k)] = __uint_as_float(hi);
+        blo[bcore_index(n, k)] = __uint_as_float(lo);
+    }
+}
+
+// The 3xTF32 product of one 128 x 32 A block (columns a_hi.. / a_lo.. of TMEM) with the N = 16 rows [16 nh, 16 nh + 16)
+// of B, into the 16 accumulator columns at d_tmem: 12 MMAs (small terms first).
+__device__ __forceinline__ void issue_gemm_half(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                                int nh) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, 16);
+    const uint64_t row_off = (uint64_t)((nh * 2 * B_SBO) >> 4);
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) {
+        const uint32_t acol = (pr == 0) ? a_lo : a_hi;                 // lo*hi, hi*lo, hi*hi
+        const uint64_t bd = ((pr == 1) ? b_lo : b_hi) + row_off;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            mma_tf32_ts(d_tmem, acol + ks * 8, bd + (uint64_t)((ks * 2 * B_LBO) >> 4), idesc, (pr | ks) != 0 ? 1u : 0u);
+    }
+}
+
+// shared-memory layout of the forward kernel (floats, after CF::SM_PARAMS rounded up to 32)
+template <class CF>
+struct FwdSmem {
+    static constexpr int OFF_BHI = (CF::SM_PARAMS + 31) & ~31;
+    static constexpr int OFF_BLO = OFF_BHI + H * H;
+    static constexpr int OFF_EXCH = OFF_BLO + H * H;          // [C][TP] partial output dots of warpgroup 1
+    static constexpr int OFF_OUT = OFF_EXCH + CF::C * TP;      // [TP][C] tile output in external component order
+    static constexpr int FLOATS = OFF_OUT + CF::C * TP;
+};
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <class CF>
+__global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
+    static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");
+    static_assert(3 * CF::C * 32 <= (int)TMEM_COLS, "A hi, A lo and D must fit the 512 TMEM columns");
+    constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
+    constexpr uint32_t COL_AHI = 0, COL_ALO = C * 32, COL_D = 2 * C * 32;
+    using L = FwdSmem<CF>;
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_slot;
+    float* bhi = sm + L::OFF_BHI;
+    float* blo = sm + L::OFF_BLO;
+    float* exch = sm + L::OFF_EXCH;
+    float* outN = sm + L::OFF_OUT;
+
+    const int tid = threadIdx.x, warp = warp_uniform();
+    const int g = tid >> 7;                 // warpgroup = unit half
+    const int r = tid & 127;                // point row of the tile = TMEM lane
+    const int j0 = 16 * g;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
+    const int im = a.sub_ids[sp];
+    const int xd = a.xd;
+    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < xd) {
+            const float lo = ss[d], hi = ss[xd + d];
+            mu[d] = (hi + lo) * 0.5f;
+            isd[d] = 1.0f / ((hi - lo) * 0.5f);
+        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
+    }
+    const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
+    const float* prow = a.params + (int64_t)im * a.P;
+    fast_load_params<CF, NT>(sm, prow, xd, isd, a.axis, false);
+    stage_b(bhi, blo, prow + H * xd + H, H, 1, tid);           // B[n = j][k] = W1[j][k]
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();                                       // B is read by the tensor core (async proxy)
+    __syncthreads();
+    // the allocation comes after the staging so that a CTA waiting for the previous one's columns has its prologue done
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const uint64_t bdesc_hi = make_smem_desc(smem_u32(bhi), B_LBO, B_SBO);
+    const uint64_t bdesc_lo = make_smem_desc(smem_u32(blo), B_LBO, B_SBO);
+
+    // software prefetch of the next tile's point (pair -> point index -> coordinates)
+    int pf_pt = 0;
+    float pf_x[3] = {0.0f, 0.0f, 0.0f};
+    auto load_idx = [&](int t0n) {
+        if (t0n < count) pf_pt = a.spair_point[first + t0n + (r < min(TP, count - t0n) ? r : 0)];
+    };
+    auto load_val = [&](int t0n) {
+        if (t0n < count) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
+        }
+    };
+    load_idx(0);
+    load_val(0);
+
+    uint32_t parity = 0;
+    for (int t0 = 0; t0 < count; t0 += TP, parity ^= 1) {
+        const int cnt = min(TP, count - t0);
+        float z[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
+        load_idx(t0 + TP);
+
+        // ---- layer 0 for this thread's 16 units: tanh jets -> A (hi, lo) in tensor memory -------------------
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int jb = j0 + 8 * ch;
+            float hv[8][C];
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + jb + 4 * q4);
+                const float4 w1 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + H + jb + 4 * q4);
+                const float4 w2 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + 2 * H + jb + 4 * q4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sm + CF::SM_B0 + jb + 4 * q4);
+                float4 wd[NS > 0 ? NS : 1];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) wd[s] = *reinterpret_cast<const float4*>(sm + CF::SM_W0D + s * H + jb + 4 * q4);
+                const float w0a[4] = {w0.x, w0.y, w0.z, w0.w}, w1a[4] = {w1.x, w1.y, w1.z, w1.w};
+                const float w2a[4] = {w2.x, w2.y, w2.z, w2.w}, b0a[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float (&av)[C] = hv[4 * q4 + e];
+                    av[0] = fmaf(w2a[e], z[2], fmaf(w1a[e], z[1], fmaf(w0a[e], z[0], b0a[e])));
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const float wv = e == 0 ? wd[s].x : (e == 1 ? wd[s].y : (e == 2 ? wd[s].z : wd[s].w));
+                        if (s < NA2) { av[1 + 2 * s] = wv; av[2 + 2 * s] = 0.0f; }
+                        else av[1 + 2 * NA2 + (s - NA2)] = wv;
+                    }
+                    fast_tanh_jets<CF>(av);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tf32_split(hv[e][c], hi[e], lo[e]);
+                tmem_st8(tbase + lane_base + COL_AHI + c * 32 + jb, hi);
+                tmem_st8(tbase + lane_base + COL_ALO + c * 32 + jb, lo);
+            }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();                                         // A complete; previous tile's D fully read
+
+        // ---- hidden GEMM on the tensor core: D[c] = A[c] * W1^T, unit half 0 first ---------------------------
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        issue_gemm_half(tbase + COL_D + c * 32 + nh * 16, tbase + COL_AHI + c * 32, tbase + COL_ALO + c * 32,
+                                        bdesc_hi, bdesc_lo, nh);
+                    mma_commit(&mma_bar[nh]);
+                }
+            }
+            __syncwarp();
+        }
+        load_val(t0 + TP);
+
+        // ---- epilogue of this thread's unit half: bias, tanh jets, cache, partial output dot ------------------
+        mbar_wait_or_trap(&mma_bar[g], parity);
+        tc_fence_after();
+        float up[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) up[c] = 0.0f;
+        float* cb = nullptr;
+        int cntb = 0;
+        if (a.cache != nullptr && r < cnt) {
+            constexpr int TPB = CF::TPB;                          // the reverse kernel's tile (its cache layout)
+            const int off = t0 + r;
+            const int t0b = (off / TPB) * TPB;
+            cntb = min(TPB, count - t0b);
+            cb = a.cache + (int64_t)(first + t0b) * (H * C) + (off - t0b);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int jb = j0 + 8 * ch;
+            uint32_t v[C][8];
+#pragma unroll
+            for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + COL_D + c * 32 + jb, v[c]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float acc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = __uint_as_float(v[c][e]);
+                acc[0] += sm[CF::SM_B1 + jb + e];
+                fast_tanh_jets<CF>(acc);
+                if (cb != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) cb[((jb + e) * C + c) * cntb] = acc[c];
+                }
+                const float wl = sm[CF::SM_WL + jb + e];
+#pragma unroll
+                for (int c = 0; c < C; ++c) up[c] = fmaf(wl, acc[c], up[c]);
+            }
+        }
+        if (g == 1) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) exch[c * TP + r] = up[c];
+        }
+        mbar_wait_or_trap(&mma_bar[1], parity);                  // every MMA of the tile is done: A may be rewritten
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- output layer, window jets and Leibniz product per point (warpgroup 0) ---------------------------
+        if (g == 0) {
+            float u[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) u[c] = un_sd * (up[c] + exch[c * TP + r] + (c == 0 ? sm[CF::SM_BL] : 0.0f));
+            u[0] += un_mu;
+            float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
+            fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
+            float* o = outN + r * C;
+            o[a.ext[0]] = u[0] * w;
+#pragma unroll
+            for (int s = 0; s < NA2; ++s) {
+                const float u1 = u[1 + 2 * s], u2 = u[2 + 2 * s];
+                o[a.ext[1 + 2 * s]] = u1 * w + u[0] * w1[s];
+                o[a.ext[2 + 2 * s]] = u2 * w + 2.0f * u1 * w1[s] + u[0] * w2[s];
+            }
+#pragma unroll
+            for (int s = 0; s < NA1; ++s) {
+                const int c = 1 + 2 * NA2 + s;
+                o[a.ext[c]] = u[c] * w + u[0] * w1[NA2 + s];
+            }
+        }
+        __syncthreads();
+        float* dst = a.pair_out + (int64_t)(first + t0) * C;
+        for (int i = tid; i < cnt * C; i += NT) dst[i] = outN[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);
+}
+
+}  // namespace fbptc
+
+// launchers of the tensor family (fbp_tc.cu)
+int fbp_tc_forward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st);

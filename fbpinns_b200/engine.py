@@ -57,7 +57,12 @@ class Plan:
 
     def set_kernel(self, kernel):
         lib = _lib.load()
-        mode = {"auto": 0, "generic": 1, "tiled": 2}[kernel]
+        mode = {"auto": 0, "generic": 1, "tiled": 2, "tensor": 3}[kernel]
+        self.has_tensor = bool(lib.fbp_plan_has_tensor(self._h))
+        if mode == 3 and not self.has_tensor:
+            # "tensor" on a trainer means "where an instance exists" (e.g. not for a boundary constraint with other
+            # jets); the family actually used is always visible as Plan.kernel
+            kernel, mode = "auto", 0
         check(lib.fbp_plan_set_kernel(self._h, mode), "fbp_plan_set_kernel")
         self.kernel = kernel
         self.is_fast = bool(lib.fbp_plan_is_fast(self._h)) and mode != 1

@@ -114,8 +114,11 @@ int fbp_plan_destroy(fbp_plan* plan);
 int64_t fbp_plan_param_count(const fbp_plan* plan);       /* P */
 int32_t fbp_plan_is_fast(const fbp_plan* plan);           /* 1 if a tiled kernel instance covers this plan */
 int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile (work-list granularity) */
-/* Select kernel family: 0 = auto (tiled when available), 1 = force generic, 2 = force tiled (error if none). */
+/* Select kernel family: 0 = auto (tiled when available), 1 = force generic, 2 = force tiled (error if none),
+ * 3 = tensor: the forward hidden-layer GEMMs run on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy);
+ *     needs H = 32, two hidden layers and at most 5 jet components (error otherwise).  The reverse kernel stays tiled. */
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode);
+int32_t fbp_plan_has_tensor(const fbp_plan* plan);        /* 1 if mode 3 is available for this plan */
 /* Scratch floats the generic kernels need per pair (0 for tiled plans in auto mode). */
 int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan);
 /* Floats per pair of the optional activation cache (0 if the plan's kernels do not use one).  When a cache of
@@ -215,6 +218,11 @@ int fbp_adam_step(float* d_params, float* d_mu, float* d_nu, const float* d_grad
 int fbp_fma_peak(int32_t iters, float* tflops, void* stream);
 /* The same with the packed instruction fma.rn.f32x2 (SASS FFMA2, sm_100+): 16 FMAs per thread per iteration. */
 int fbp_ffma2_peak(int32_t iters, float* tflops, void* stream);
+
+/* Self-test of the tensor family's MMA form: d_out[128][32] = d_a[128][32] * d_w[32][32]^T computed with the same
+ * tcgen05 path the mode-3 kernels use (A written row-wise into tensor memory, B through a shared-memory descriptor,
+ * 3xTF32).  `variant` = 0 for the shipped conventions; bits 0-2 probe alternatives (see fbp_tc.cu). */
+int fbp_tc_selftest(const float* d_a, const float* d_w, float* d_out, int32_t variant, void* stream);
 
 #ifdef __cplusplus
 }

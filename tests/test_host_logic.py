@@ -228,3 +228,29 @@ def test_affine_constraining_fast_path_matches_generic():
     nonaff = lambda ap, x, u: torch.tanh(x[:, 0:1]) * u ** 2
     x = torch.rand(11, 1, dtype=torch.float64)
     assert AffineConstraining.build(JetSpec(((0, ()), (0, (0,))), 1, 1), x, nonaff, {}) is None
+
+
+def test_umma_descriptors_match_cute(tmp_path):
+    """tcgen05 family (csrc/fbp_tc.cuh): the hand-encoded shared-memory / instruction descriptors and the operand
+    layout in shared memory are bit-identical with what the CuTe headers of this image define (host-side check)."""
+    import glob
+    import shutil
+    import subprocess
+    import site
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    inc = None
+    for sp in site.getsitepackages():
+        hits = glob.glob(os.path.join(sp, "*", "data", "cutlass", "include")) + glob.glob(os.path.join(sp, "*", "3rdparty", "cutlass", "include"))
+        hits = [h for h in hits if os.path.exists(os.path.join(h, "cute", "arch", "mma_sm100_desc.hpp"))]
+        if hits:
+            inc = hits[0]
+            break
+    if inc is None or shutil.which("nvcc") is None:
+        pytest.skip("no CuTe sm_100 headers / nvcc in this environment")
+    exe = str(tmp_path / "umma_check")
+    cmd = ["nvcc", "-std=c++17", "-I" + inc, "-I" + os.path.join(root, "fbpinns_b200", "csrc"), "-gencode",
+           "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr", "-o", exe, os.path.join(root, "tests", "tools", "umma_desc_check.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr

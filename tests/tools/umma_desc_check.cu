@@ -1,0 +1,42 @@
+// Host-side check that the hand-encoded UMMA descriptors and the shared-memory operand layout of
+// fbpinns_b200/csrc/fbp_tc.cuh agree with the definitions in the CUTLASS/CuTe headers shipped in this image
+// (cute/arch/mma_sm100_desc.hpp, cute/atom/mma_traits_sm100.hpp).  Prints "OK" and exits 0 on agreement.
+// Built and run by tests/test_host_logic.py::test_umma_descriptors_match_cute (no GPU needed).
+#include <cstdio>
+#include <cute/tensor.hpp>
+#include <cute/arch/mma_sm100_desc.hpp>
+#include <cute/atom/mma_traits_sm100.hpp>
+#include "fbp_tc.cuh"
+
+using namespace cute;
+
+int main() {
+    int bad = 0;
+    using T = tfloat32_t;
+    // canonical K-major SWIZZLE_NONE layout of a 32 x 32 tf32 operand, K atoms innermost
+    auto lay = tile_to_shape(UMMA::Layout_K_INTER_Atom<T>{}, Shape<_32, _32>{}, Step<_2, _1>{});
+    for (int n = 0; n < 32; ++n)
+        for (int k = 0; k < 32; ++k)
+            if ((int)lay(n, k) != fbptc::bcore_index(n, k)) ++bad;
+    if (bad) printf("layout: %d elements differ from the CuTe canonical layout\n", bad);
+    // the strides make_umma_desc<Major::K> would put into the descriptor
+    auto u128 = recast_layout<T, uint128_t>(lay.layout_b());
+    auto canon = logical_divide(u128, Tile<Layout<_8, _1>, Layout<_2, _1>>{});
+    const uint32_t sbo = (uint32_t)stride<0, 1>(canon) * 16, lbo = (uint32_t)stride<1, 0>(canon) * 16;
+    if (sbo != fbptc::B_SBO || lbo != fbptc::B_LBO) { printf("strides: cute SBO %u LBO %u, ours %u %u\n", sbo, lbo, fbptc::B_SBO, fbptc::B_LBO); ++bad; }
+    for (uint32_t addr : {0x0u, 0x12340u, 0x37ff0u}) {
+        UMMA::SmemDescriptor d;
+        d.version_ = 1; d.lbo_mode_ = 0; d.layout_type_ = uint8_t(UMMA::LayoutType::SWIZZLE_NONE); d.base_offset_ = 0;
+        d.start_address_ = (uint16_t)(addr >> 4); d.leading_byte_offset_ = (uint16_t)(lbo >> 4); d.stride_byte_offset_ = (uint16_t)(sbo >> 4);
+        const uint64_t ours = fbptc::make_smem_desc(addr, fbptc::B_LBO, fbptc::B_SBO);
+        if (d.desc_ != ours) { printf("smem desc @%x: cute %016llx ours %016llx\n", addr, (unsigned long long)d.desc_, (unsigned long long)ours); ++bad; }
+    }
+    auto i16 = UMMA::make_instr_desc<T, T, float, 128, 16, UMMA::Major::K, UMMA::Major::K>();
+    auto i32 = UMMA::make_instr_desc<T, T, float, 128, 32, UMMA::Major::K, UMMA::Major::K>();
+    if (i16.desc_ != fbptc::make_idesc_tf32(128, 16) || i32.desc_ != fbptc::make_idesc_tf32(128, 32)) {
+        printf("instr desc: cute %08x %08x ours %08x %08x\n", (unsigned)i16.desc_, (unsigned)i32.desc_, fbptc::make_idesc_tf32(128, 16), fbptc::make_idesc_tf32(128, 32));
+        ++bad;
+    }
+    printf(bad ? "MISMATCH\n" : "OK\n");
+    return bad ? 1 : 0;
+}
