@@ -60,7 +60,7 @@ static void fill_args(const fbp_plan* plan, const fbp_takes_view* tv, const floa
     a.x = d_x; a.params = d_params; a.sub_static = d_sub_static;
     a.sub_ids = tv->d_sub_ids; a.spair_point = tv->d_spair_point; a.spair_row = tv->d_spair_row; a.items = tv->d_items;
     a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr; a.cache = nullptr; a.order = nullptr;
-    a.xd = plan->dev.xd; a.P = plan->dev.P;
+    a.xd = plan->dev.xd; a.P = plan->dev.P; a.dbg = 0;
     for (int i = 0; i < FBP_MAX_XD; ++i) a.axis[i] = plan->fast.axis[i];
     for (int i = 0; i < FBP_MAX_COMP; ++i) a.ext[i] = plan->fast.ext[i];
 }

@@ -51,6 +51,7 @@ struct FastArgs {
     float* cache;        // optional [s][H*C]: jets of the last hidden layer, written by the forward kernel per reverse
                          // tile as [H][C][cnt] at float offset (first pair of the tile)*H*C, read back by the reverse
     int xd, P;
+    int dbg;                // timing-experiment switches of the tensor family (0 in production)
     int axis[FBP_MAX_XD];   // slot -> axis (NA2 slots first)
     int ext[FBP_MAX_COMP];  // internal component -> external component index
 };

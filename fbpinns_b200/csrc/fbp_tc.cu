@@ -9,6 +9,8 @@ using namespace fbptc;
 // `variant` lets a hardware session probe descriptor conventions without rebuilding:
 //   bit 0: swap LBO and SBO in the descriptor          bit 1: descriptor version field 0 instead of 1
 //   bit 2: single TF32 pass (hi*hi only; expected error ~1e-3, distinguishes "wrong layout" from "wrong split")
+//   bit 3: the lo parts (A and B) are passed as raw FP32 bit patterns (does the tensor core ignore the low 13 bits?)
+//   bit 4: the hi parts are truncated (one LOP3) instead of rounded to nearest
 // -----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                             float* __restrict__ out, int variant) {
@@ -21,6 +23,16 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(const float* __restr
     constexpr uint32_t COL_AHI = 0, COL_ALO = 32, COL_D = 64;
 
     stage_b(bhi, blo, W, H, 1, tid);
+    if (variant & 24) {
+        for (int i = tid; i < H * H; i += NT) {
+            const int n = i >> 5, k = i & 31;
+            const float x = W[i];
+            const uint32_t hi = (variant & 16) ? (__float_as_uint(x) & 0xffffe000u) : tf32_rn(x);
+            const float lo = x - __uint_as_float(hi);
+            bhi[bcore_index(n, k)] = __uint_as_float(hi);
+            blo[bcore_index(n, k)] = (variant & 8) ? lo : __uint_as_float(tf32_rn(lo));
+        }
+    }
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
@@ -38,7 +50,15 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(const float* __restr
     for (int ch = 0; ch < 2; ++ch) {
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) tf32_split(A[r * H + j0 + 8 * ch + e], hi[e], lo[e]);
+        for (int e = 0; e < 8; ++e) {
+            const float x = A[r * H + j0 + 8 * ch + e];
+            tf32_split(x, hi[e], lo[e]);
+            if (variant & 24) {
+                hi[e] = (variant & 16) ? (__float_as_uint(x) & 0xffffe000u) : tf32_rn(x);
+                const float l = x - __uint_as_float(hi[e]);
+                lo[e] = (variant & 8) ? __float_as_uint(l) : tf32_rn(l);
+            }
+        }
         tmem_st8(tbase + lane_base + COL_AHI + j0 + 8 * ch, hi);
         tmem_st8(tbase + lane_base + COL_ALO + j0 + 8 * ch, lo);
     }
@@ -95,17 +115,31 @@ int fbp_tc_supported(const FastSpec& f, int C) {
     return key == 0 || key == 1 || key == 4 || key == 5 || key == 8;
 }
 
-template <class CF>
-static int tc_forward_one(const FastArgs& a, int grid, cudaStream_t st) {
-    constexpr size_t bytes = sizeof(float) * FwdSmem<CF>::FLOATS;
+#include <cstdlib>
+// FBP_TC_NWG = 2 | 4: warpgroups per CTA (A/B knob);  FBP_TC_DEBUG: timing-experiment bits (see tc_forward_kernel)
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+template <class CF, int NWG>
+static int tc_forward_nwg(FastArgs a, int grid, cudaStream_t st) {
+    constexpr size_t bytes = sizeof(float) * FwdSmem<CF, NWG>::FLOATS;
     static bool configured = false;
     if (!configured) {
-        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<CF, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = true;
     }
-    tc_forward_kernel<CF><<<grid, NT, bytes, st>>>(a);
+    a.dbg = env_int("FBP_TC_DEBUG", 0);
+    tc_forward_kernel<CF, NWG><<<grid, 128 * NWG, bytes, st>>>(a);
     FBP_LAUNCH_CHECK();
     return 0;
+}
+
+template <class CF>
+static int tc_forward_one(const FastArgs& a, int grid, cudaStream_t st) {
+    if (env_int("FBP_TC_NWG", 2) == 4) return tc_forward_nwg<CF, 4>(a, grid, st);
+    return tc_forward_nwg<CF, 2>(a, grid, st);
 }
 
 int fbp_tc_forward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st) {

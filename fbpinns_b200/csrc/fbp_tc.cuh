@@ -147,8 +147,9 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
 }
 
 // Stage a [32][32] matrix B[n][k] = src[n * sn + k * sk] (hi and lo TF32 parts) in the canonical layout.
-__device__ __forceinline__ void stage_b(float* bhi, float* blo, const float* __restrict__ src, int sn, int sk, int tid) {
-    for (int i = tid; i < H * H; i += NT) {
+__device__ __forceinline__ void stage_b(float* bhi, float* blo, const float* __restrict__ src, int sn, int sk, int tid,
+                                        int nthreads = NT) {
+    for (int i = tid; i < H * H; i += nthreads) {
         const int n = i >> 5, k = i & 31;
         uint32_t hi, lo;
         tf32_split(src[n * sn + k * sk], hi, lo);
@@ -174,25 +175,30 @@ __device__ __forceinline__ void issue_gemm_half(uint32_t d_tmem, uint32_t a_hi, 
 }
 
 // shared-memory layout of the forward kernel (floats, after CF::SM_PARAMS rounded up to 32)
-template <class CF>
+template <class CF, int NWG>
 struct FwdSmem {
     static constexpr int OFF_BHI = (CF::SM_PARAMS + 31) & ~31;
     static constexpr int OFF_BLO = OFF_BHI + H * H;
-    static constexpr int OFF_EXCH = OFF_BLO + H * H;          // [C][TP] partial output dots of warpgroup 1
-    static constexpr int OFF_OUT = OFF_EXCH + CF::C * TP;      // [TP][C] tile output in external component order
+    static constexpr int OFF_EXCH = OFF_BLO + H * H;                    // [NWG-1][C][TP] partial output dots of warpgroups 1..
+    static constexpr int OFF_OUT = OFF_EXCH + (NWG - 1) * CF::C * TP;    // [TP][C] tile output in external component order
     static constexpr int FLOATS = OFF_OUT + CF::C * TP;
 };
 
 // =====================================================================================================
 // forward
 // =====================================================================================================
-template <class CF>
-__global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
+// NWG warpgroups of 128 point rows; warpgroup g owns the hidden units [UPT g, UPT (g + 1)), UPT = 32 / NWG.
+// a.dbg (timing experiments only, results are then wrong): 2 = no MMA issue / waits, 4 = no layer 0 / A stores,
+// 8 = no tanh jets in the epilogue.
+template <class CF, int NWG>
+__global__ void __launch_bounds__(128 * NWG, 1) tc_forward_kernel(FastArgs a) {
     static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");
     static_assert(3 * CF::C * 32 <= (int)TMEM_COLS, "A hi, A lo and D must fit the 512 TMEM columns");
+    static_assert(NWG == 2 || NWG == 4, "2 or 4 warpgroups");
+    constexpr int NT = 128 * NWG, UPT = 32 / NWG, NCH = UPT / 8;
     constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
     constexpr uint32_t COL_AHI = 0, COL_ALO = C * 32, COL_D = 2 * C * 32;
-    using L = FwdSmem<CF>;
+    using L = FwdSmem<CF, NWG>;
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t mma_bar[2];
     __shared__ uint32_t tmem_slot;
@@ -202,9 +208,11 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
     float* outN = sm + L::OFF_OUT;
 
     const int tid = threadIdx.x, warp = warp_uniform();
-    const int g = tid >> 7;                 // warpgroup = unit half
+    const int g = tid >> 7;                 // warpgroup
     const int r = tid & 127;                // point row of the tile = TMEM lane
-    const int j0 = 16 * g;
+    const int j0 = UPT * g;
+    const int nhalf = j0 >> 4;              // which of the two MMA commits covers this thread's units
+    const int dbg = a.dbg;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
     const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
     const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
     const float* prow = a.params + (int64_t)im * a.P;
     fast_load_params<CF, NT>(sm, prow, xd, isd, a.axis, false);
-    stage_b(bhi, blo, prow + H * xd + H, H, 1, tid);           // B[n = j][k] = W1[j][k]
+    stage_b(bhi, blo, prow + H * xd + H, H, 1, tid, NT);       // B[n = j][k] = W1[j][k]
     if (tid == 0) {
         mbar_init(&mma_bar[0], 1);
         mbar_init(&mma_bar[1], 1);
@@ -265,8 +273,9 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
         load_idx(t0 + TP);
 
         // ---- layer 0 for this thread's 16 units: tanh jets -> A (hi, lo) in tensor memory -------------------
+        if (!(dbg & 4))
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+        for (int ch = 0; ch < NCH; ++ch) {
             const int jb = j0 + 8 * ch;
             float hv[8][C];
 #pragma unroll
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
         __syncthreads();                                         // A complete; previous tile's D fully read
 
         // ---- hidden GEMM on the tensor core: D[c] = A[c] * W1^T, unit half 0 first ---------------------------
-        if (warp == 0) {
+        if (warp == 0 && !(dbg & 2)) {
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
@@ -324,7 +333,7 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
         load_val(t0 + TP);
 
         // ---- epilogue of this thread's unit half: bias, tanh jets, cache, partial output dot ------------------
-        mbar_wait_or_trap(&mma_bar[g], parity);
+        if (!(dbg & 2)) mbar_wait_or_trap(&mma_bar[nhalf], parity);
         tc_fence_after();
         float up[C];
 #pragma unroll
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
             cb = a.cache + (int64_t)(first + t0b) * (H * C) + (off - t0b);
         }
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
+        for (int ch = 0; ch < NCH; ++ch) {
             const int jb = j0 + 8 * ch;
             uint32_t v[C][8];
 #pragma unroll
@@ -351,7 +360,7 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) acc[c] = __uint_as_float(v[c][e]);
                 acc[0] += sm[CF::SM_B1 + jb + e];
-                fast_tanh_jets<CF>(acc);
+                if (!(dbg & 8)) fast_tanh_jets<CF>(acc);
                 if (cb != nullptr) {
 #pragma unroll
                     for (int c = 0; c < C; ++c) cb[((jb + e) * C + c) * cntb] = acc[c];
@@ -361,11 +370,11 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
                 for (int c = 0; c < C; ++c) up[c] = fmaf(wl, acc[c], up[c]);
             }
         }
-        if (g == 1) {
+        if (g > 0) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) exch[c * TP + r] = up[c];
+            for (int c = 0; c < C; ++c) exch[((g - 1) * C + c) * TP + r] = up[c];
         }
-        mbar_wait_or_trap(&mma_bar[1], parity);                  // every MMA of the tile is done: A may be rewritten
+        if (!(dbg & 2)) mbar_wait_or_trap(&mma_bar[1], parity);  // every MMA of the tile is done: A may be rewritten
         tc_fence_before();
         __syncthreads();
 
@@ -373,7 +382,12 @@ __global__ void __launch_bounds__(NT, 1) tc_forward_kernel(FastArgs a) {
         if (g == 0) {
             float u[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) u[c] = un_sd * (up[c] + exch[c * TP + r] + (c == 0 ? sm[CF::SM_BL] : 0.0f));
+            for (int c = 0; c < C; ++c) {
+                float sum = up[c];
+#pragma unroll
+                for (int gg = 1; gg < NWG; ++gg) sum += exch[((gg - 1) * C + c) * TP + r];
+                u[c] = un_sd * (sum + (c == 0 ? sm[CF::SM_BL] : 0.0f));
+            }
             u[0] += un_mu;
             float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
             fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
