@@ -337,7 +337,7 @@ def run_ours(args):
                        if not args.small else "SMALL cfg5 16x16 subdomains 256x256 grid (debug)",
                        "layers": list(layer_sizes), "subdomains": m, "points": n_points_global,
                        "pairs_this_rank": s_local, "parallelism": f"subdomain-slabs x{world}" if world > 1 else "single GPU",
-                       "cuda_graph": tr.update.graph is not None, "kernel_family": ("tensor+tiled" if ev.plan.kernel == "tensor" else "tiled") if ev.plan.is_fast else "generic",
+                       "cuda_graph": tr.update.graph is not None, "kernel_family": {"generic": "generic", "tiled": "tiled", "tensor": "tensor forward (tcgen05 3xTF32) + tiled reverse"}[ev.plan.forward_family],
                        "l2": "per-step working set (pair jets 175 MB + indices 105 MB) exceeds the 126 MB L2; "
                              "per-kernel timings flush L2 with a 256 MB write between launches"},
             "ujs_point_evals_per_sec": int(tr.x_batch_global.shape[0]) * steps_per_s,
@@ -354,8 +354,12 @@ def run_ours(args):
                          "peak_ffma": fma_scalar, "peak_ffma2": fma_packed, "peak_nominal": nominal,
                          "launch_ms": bwd_ms, "launch_ms_best": bwd_best, "flops_per_launch": 2.0 * f_fwd * s_active,
                          "traffic": traffic,
-                         "forward": {"kernel": "fast_forward_kernel", "achieved": fwd_tf, "frac": fwd_tf / fma_peak if fma_peak else None,
-                                     "launch_ms": fwd_ms, "flops_per_launch": float(f_fwd * s_local)},
+                         "forward": {"kernel": "tc_forward_kernel" if ev.plan.forward_family == "tensor" else "fast_forward_kernel",
+                                     "achieved": fwd_tf, "frac": fwd_tf / fma_peak if fma_peak else None,
+                                     "launch_ms": fwd_ms, "flops_per_launch": float(f_fwd * s_local),
+                                     "note": ("hidden GEMM on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy); the "
+                                              "fraction is still algorithmic FP32 flops over the FP32 FMA peak")
+                                             if ev.plan.forward_family == "tensor" else None},
                          "step_frac_of_fp32_peak": step_tf / (fma_peak * world) if fma_peak else None,
                          "hbm_algorithmic_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9,
                          "hbm_peak_gbs": peaks.get("hbm_gbs")},

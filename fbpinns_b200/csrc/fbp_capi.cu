@@ -1,6 +1,7 @@
 // C ABI of libfbpinn_b200 (see include/fbpinn_b200.h): plan management, validation and dispatch between the
 // tiled (fbp_fast_*.cu) and generic (fbp_generic.cu) kernel families.
 #include "fbp_common.cuh"
+#include <stdlib.h>
 
 #include <stdarg.h>
 #include <string.h>
@@ -96,6 +97,10 @@ int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
     }
     p->fast_id = fbp_fast_lookup(d, &p->fast);
     p->tc_ok = p->fast_id >= 0 && fbp_tc_supported(p->fast, p->dev.C) != 0;
+    {   // instance validated on B200 (profiles/r1f_tc_bringup.md): two second-order axes, C = 5 (cfg 5)
+        const char* e = getenv("FBP_TC_AUTO");
+        p->tc_auto = p->tc_ok && p->fast.na2 == 2 && p->fast.na1 == 0 && !(e && e[0] == '0');
+    }
     p->mode = 0;
     *out = p;
     return 0;
@@ -111,6 +116,10 @@ int32_t fbp_plan_is_fast(const fbp_plan* plan) { return plan && plan->fast_id >=
 int32_t fbp_plan_tile_points(const fbp_plan* plan) { return (plan && plan->use_fast()) ? plan->fast.tile_points : 128; }
 
 int32_t fbp_plan_has_tensor(const fbp_plan* plan) { return plan && plan->fast_id >= 0 && plan->tc_ok ? 1 : 0; }
+int32_t fbp_plan_forward_family(const fbp_plan* plan) {
+    if (!plan) return -1;
+    return !plan->use_fast() ? 0 : (plan->use_tc() ? 2 : 1);
+}
 
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
     FBP_REQUIRE(plan, "fbp_plan_set_kernel: null plan");

@@ -138,8 +138,9 @@ static int tc_forward_nwg(FastArgs a, int grid, cudaStream_t st) {
 
 template <class CF>
 static int tc_forward_one(const FastArgs& a, int grid, cudaStream_t st) {
-    if (env_int("FBP_TC_NWG", 2) == 4) return tc_forward_nwg<CF, 4>(a, grid, st);
-    return tc_forward_nwg<CF, 2>(a, grid, st);
+    // 4 warpgroups measured faster than 2 (1.995 vs 2.238 ms on cfg 5, profiles/r1f_tc_bringup.md)
+    if (env_int("FBP_TC_NWG", 4) == 2) return tc_forward_nwg<CF, 2>(a, grid, st);
+    return tc_forward_nwg<CF, 4>(a, grid, st);
 }
 
 int fbp_tc_forward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st) {

@@ -65,6 +65,7 @@ class Plan:
             kernel, mode = "auto", 0
         check(lib.fbp_plan_set_kernel(self._h, mode), "fbp_plan_set_kernel")
         self.kernel = kernel
+        self.forward_family = ("generic", "tiled", "tensor")[int(lib.fbp_plan_forward_family(self._h))]
         self.is_fast = bool(lib.fbp_plan_is_fast(self._h)) and mode != 1
         self.tile_points = int(lib.fbp_plan_tile_points(self._h))
         self.scratch_per_pair = int(lib.fbp_plan_scratch_per_pair(self._h))

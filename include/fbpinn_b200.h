@@ -114,11 +114,13 @@ int fbp_plan_destroy(fbp_plan* plan);
 int64_t fbp_plan_param_count(const fbp_plan* plan);       /* P */
 int32_t fbp_plan_is_fast(const fbp_plan* plan);           /* 1 if a tiled kernel instance covers this plan */
 int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile (work-list granularity) */
-/* Select kernel family: 0 = auto (tiled when available), 1 = force generic, 2 = force tiled (error if none),
+/* Select kernel family: 0 = auto (tiled when available; the tensor forward where its instance has been validated on
+ * hardware, unless the environment says FBP_TC_AUTO=0), 1 = force generic, 2 = force tiled (error if none),
  * 3 = tensor: the forward hidden-layer GEMMs run on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy);
  *     needs H = 32, two hidden layers and at most 5 jet components (error otherwise).  The reverse kernel stays tiled. */
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode);
 int32_t fbp_plan_has_tensor(const fbp_plan* plan);        /* 1 if mode 3 is available for this plan */
+int32_t fbp_plan_forward_family(const fbp_plan* plan);    /* family fbp_forward will use: 0 generic, 1 tiled, 2 tensor */
 /* Scratch floats the generic kernels need per pair (0 for tiled plans in auto mode). */
 int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan);
 /* Floats per pair of the optional activation cache (0 if the plan's kernels do not use one).  When a cache of

@@ -212,12 +212,14 @@ def test_activation_cache_matches_recompute(name):
     torch.cuda.synchronize()
     assert torch.equal(u1, u2)
     assert torch.isfinite(g1).all()
-    assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 2e-6
+    # 5e-6: where the forward kernel is the tensor-core one, the cached hidden jets are 3xTF32 results (measured 7e-7
+    # from the FP32 ones) while the recompute path is pure FP32; each path is held to 1e-5 against the oracle elsewhere
+    assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 5e-6
     # a second step with different parameters must refresh the cache (no stale activations)
     p2 = params * 1.01
     ev.forward(p2); ev.backward(ubar, p2, g1, accumulate=False)
     ev2.forward(p2); ev2.backward(ubar, p2, g2, accumulate=False)
-    assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 2e-6
+    assert common.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) < 5e-6
 
 
 def test_multilevel_decomposition_npou2_matches_oracle():
