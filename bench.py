@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", default="2,32,32,1", help="FCN layer sizes (sweep: 2,32,1 / 2,64,64,1)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled", "tensor"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tiled", "tensor", "tensor-full"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-rebuild", action="store_true")

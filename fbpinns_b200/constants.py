@@ -97,7 +97,7 @@ class Constants(ConstantsBase):
         # B200 engine options (not in the reference)
         self.device = "cuda:0"
         self.use_cuda_graph = True       # capture the whole step between active-set changes
-        self.kernel = "auto"             # "auto" | "generic" | "tiled" | "tensor" (tcgen05 where an instance exists)
+        self.kernel = "auto"             # "auto" | "generic" | "tiled" | "tensor" | "tensor-full" (tcgen05 where an instance exists)
 
         self.hostname = socket.gethostname().lower()
 

@@ -123,9 +123,9 @@ int32_t fbp_plan_forward_family(const fbp_plan* plan) {
 
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
     FBP_REQUIRE(plan, "fbp_plan_set_kernel: null plan");
-    FBP_REQUIRE(mode >= 0 && mode <= 3, "fbp_plan_set_kernel: mode must be 0, 1, 2 or 3");
+    FBP_REQUIRE(mode >= 0 && mode <= 4, "fbp_plan_set_kernel: mode must be 0 .. 4");
     FBP_REQUIRE(mode != 2 || plan->fast_id >= 0, "fbp_plan_set_kernel: no tiled kernel instance for this plan");
-    FBP_REQUIRE(mode != 3 || (plan->fast_id >= 0 && plan->tc_ok),
+    FBP_REQUIRE((mode != 3 && mode != 4) || (plan->fast_id >= 0 && plan->tc_ok),
                 "fbp_plan_set_kernel: no tensor (tcgen05) kernel instance for this plan (needs H = 32, two hidden layers, "
                 "at most 5 jet components)");
     plan->mode = mode;
@@ -134,6 +134,7 @@ int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
 
 int64_t fbp_plan_cache_per_pair(const fbp_plan* plan) {
     if (!plan) return -1;
+    if (plan->use_tc_bwd()) return 0;      // the tensor reverse kernel recomputes the hidden layer on the tensor core
     return (plan->use_fast() && plan->fast.nhid == 2) ? (int64_t)plan->fast.H * plan->dev.C : 0;
 }
 

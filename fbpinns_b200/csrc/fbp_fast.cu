@@ -1,5 +1,5 @@
 // Tiled kernel family: plan matching, launch glue and the deterministic partial-gradient reduction.
-#include "fbp_tc.cuh"
+#include "fbp_tc_bwd.cuh"
 
 __global__ void fast_grad_reduce_kernel(const float* __restrict__ gpart, const int32_t* __restrict__ sub_item_off,
                                         int m_active, int P, float* __restrict__ grads, int accumulate) {
@@ -108,7 +108,10 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
         a.gpart = d_gpart;
         a.cache = const_cast<float*>(d_cache);
         a.order = tv->d_item_order_bwd;
-        if (int rc = dispatch(plan, true, a, tv->n_items_active, stream)) return rc;
+        if (plan->use_tc_bwd()) {
+            a.cache = nullptr;
+            if (int rc = fbp_tc_backward_launch(plan->fast, a, tv->n_items_active, stream)) return rc;
+        } else if (int rc = dispatch(plan, true, a, tv->n_items_active, stream)) return rc;
     }
     if (!run_reduce) return 0;
     const int64_t total = (int64_t)tv->m_active * plan->dev.P;

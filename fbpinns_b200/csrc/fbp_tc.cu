@@ -1,5 +1,5 @@
 // tcgen05 ("tensor") kernel family: instantiations, launch glue and the MMA self-test.
-#include "fbp_tc.cuh"
+#include "fbp_tc_bwd.cuh"
 
 using namespace fbptc;
 
@@ -153,5 +153,33 @@ int fbp_tc_forward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaSt
         default: break;
     }
     fbp_set_error("fbp_tc: no tensor-family instance for jets=(%d,%d)", f.na2, f.na1);
+    return 3;
+}
+
+template <class CF>
+static int tc_backward_one(FastArgs a, int grid, cudaStream_t st) {
+    constexpr size_t bytes = sizeof(float) * BwdSmem<CF>::FLOATS;
+    static_assert(bytes <= 227 * 1024, "reverse kernel: shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = true;
+    }
+    a.dbg = env_int("FBP_TC_DEBUG", 0);
+    tc_backward_kernel<CF><<<grid, BWD_NT, bytes, st>>>(a);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+int fbp_tc_backward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st) {
+    switch (f.na2 * 4 + f.na1) {
+        case 0: return tc_backward_one<FastCfg<32, 2, 0, 0>>(a, grid, st);
+        case 1: return tc_backward_one<FastCfg<32, 2, 0, 1>>(a, grid, st);
+        case 4: return tc_backward_one<FastCfg<32, 2, 1, 0>>(a, grid, st);
+        case 5: return tc_backward_one<FastCfg<32, 2, 1, 1>>(a, grid, st);
+        case 8: return tc_backward_one<FastCfg<32, 2, 2, 0>>(a, grid, st);
+        default: break;
+    }
+    fbp_set_error("fbp_tc: no tensor-family reverse instance for jets=(%d,%d)", f.na2, f.na1);
     return 3;
 }

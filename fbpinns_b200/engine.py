@@ -57,9 +57,9 @@ class Plan:
 
     def set_kernel(self, kernel):
         lib = _lib.load()
-        mode = {"auto": 0, "generic": 1, "tiled": 2, "tensor": 3}[kernel]
+        mode = {"auto": 0, "generic": 1, "tiled": 2, "tensor": 3, "tensor-full": 4}[kernel]
         self.has_tensor = bool(lib.fbp_plan_has_tensor(self._h))
-        if mode == 3 and not self.has_tensor:
+        if mode in (3, 4) and not self.has_tensor:
             # "tensor" on a trainer means "where an instance exists" (e.g. not for a boundary constraint with other
             # jets); the family actually used is always visible as Plan.kernel
             kernel, mode = "auto", 0

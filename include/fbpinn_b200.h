@@ -117,7 +117,8 @@ int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile
 /* Select kernel family: 0 = auto (tiled when available; the tensor forward where its instance has been validated on
  * hardware, unless the environment says FBP_TC_AUTO=0), 1 = force generic, 2 = force tiled (error if none),
  * 3 = tensor: the forward hidden-layer GEMMs run on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy);
- *     needs H = 32, two hidden layers and at most 5 jet components (error otherwise).  The reverse kernel stays tiled. */
+ *     needs H = 32, two hidden layers and at most 5 jet components (error otherwise).  The reverse kernel stays tiled.
+ * 4 = tensor forward and the warp-specialised tensor reverse kernel (no activation cache; bring-up state). */
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode);
 int32_t fbp_plan_has_tensor(const fbp_plan* plan);        /* 1 if mode 3 is available for this plan */
 int32_t fbp_plan_forward_family(const fbp_plan* plan);    /* family fbp_forward will use: 0 generic, 1 tiled, 2 tensor */

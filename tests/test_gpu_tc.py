@@ -69,12 +69,14 @@ def test_tensor_forward_matches_oracle_and_tiled(name):
         assert common.rel_err(ev_t.cache.cpu().numpy(), ev_f.cache.cpu().numpy()) < 5e-6
 
 
+@pytest.mark.parametrize("kernel", ["tensor", "tensor-full"])
 @pytest.mark.parametrize("name", ["cfg2", "cfg5"])
-def test_tensor_loss_and_grads_match_oracle(name):
+def test_tensor_loss_and_grads_match_oracle(name, kernel):
     import gpu_common
     from test_gpu_forward_backward import _make_step
     k = common.make_case(configs.CONFIGS[name](**configs.SMALL[name]), seed=0)
-    dd, inp, params = gpu_common.device_case(k, kernel="tensor")
+    dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+    assert inp.evaluators[0].plan.kernel == kernel
     step, adam, prob_flat = _make_step(k, inp, params, params.device)
     step.grads.zero_()
     loss = step.forward_loss()
@@ -88,15 +90,41 @@ def test_tensor_loss_and_grads_match_oracle(name):
         assert ew < TOL and eb < TOL, f"{name} layer {l}: grad rel err W {ew:.2e} b {eb:.2e}"
 
 
+def test_tensor_reverse_matches_tiled_with_partial_tiles_and_fixed_subdomains():
+    """tensor-full vs tiled gradients on a case with full tiles, partial tails and fixed (forward-only) subdomains"""
+    import gpu_common
+    from fbpinns_b200.schedulers import LineSchedulerRectangularND
+    c = configs.cfg5_poisson(n_sub=(5, 4), n_pts=(160, 136), n_steps=40)
+    k0 = common.make_case(c, seed=1)
+    states = [a.copy() for a in LineSchedulerRectangularND(k0.all_params, 40, point=[0.], iaxis=0) if a is not None]
+    for active in [np.ones(k0.m, dtype=int), [a for a in states if (a == 2).any()][0]]:
+        k = common.make_case(c, seed=1, active=active)
+        grads = {}
+        for kernel in ["tiled", "tensor-full"]:
+            dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+            ev = inp.evaluators[0]
+            torch.manual_seed(0)
+            ubar = torch.randn(ev.takes.n, ev.V, device=params.device)
+            g = torch.full((max(len(inp.active_ims), 1), params.shape[1]), float("nan"), device=params.device)
+            ev.forward(params)
+            ev.backward(ubar, params, g, accumulate=False)
+            torch.cuda.synchronize()
+            grads[kernel] = g.cpu().numpy()
+        assert np.isfinite(grads["tensor-full"]).all()
+        assert common.rel_err(grads["tensor-full"], grads["tiled"]) < 5e-6
+
+
 def test_tensor_training_curve_matches_tiled():
     "30 Adam steps of the reduced cfg 5 with either family: same loss curve within 1e-4 relative"
     from fbpinns_b200.trainers import FBPINNTrainer
     losses = {}
-    for kernel in ["tiled", "tensor"]:
+    for kernel in ["tiled", "tensor", "tensor-full"]:
         c = configs.cfg5_poisson(device="cuda:0", kernel=kernel, use_cuda_graph=True, **configs.SMALL["cfg5"])
         tr = FBPINNTrainer(c)
         tr.setup()
         tr.set_active(np.ones(tr.all_params["static"]["decomposition"]["m"], dtype=int))
         losses[kernel] = [float(tr.step()) for _ in range(30)]
-    a, b = np.array(losses["tiled"]), np.array(losses["tensor"])
-    assert np.all(np.abs(a - b) <= 1e-4 * np.abs(a)), (a[-3:], b[-3:])
+    a = np.array(losses["tiled"])
+    for kernel in ["tensor", "tensor-full"]:
+        b = np.array(losses[kernel])
+        assert np.all(np.abs(a - b) <= 1e-4 * np.abs(a)), (kernel, a[-3:], b[-3:])
