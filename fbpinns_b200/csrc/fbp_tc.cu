@@ -137,7 +137,21 @@ static int tc_forward_nwg(FastArgs a, int grid, cudaStream_t st) {
 }
 
 template <class CF>
+static int tc_forward_v2(FastArgs a, int grid, cudaStream_t st) {
+    constexpr size_t bytes = sizeof(float) * FwdSmem<CF, 4>::FLOATS;
+    static bool configured = false;
+    if (!configured) {
+        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel2<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = true;
+    }
+    tc_forward_kernel2<CF><<<grid, 512, bytes, st>>>(a);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+template <class CF>
 static int tc_forward_one(const FastArgs& a, int grid, cudaStream_t st) {
+    if (env_int("FBP_TC_FWD", 1) == 2) return tc_forward_v2<CF>(a, grid, st);     // pipelined variant (bring-up)
     // 4 warpgroups measured faster than 2 (1.995 vs 2.238 ms on cfg 5, profiles/r1f_tc_bringup.md)
     if (env_int("FBP_TC_NWG", 4) == 2) return tc_forward_nwg<CF, 2>(a, grid, st);
     return tc_forward_nwg<CF, 4>(a, grid, st);

@@ -71,6 +71,14 @@ __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) 
     lo = tf32_rn(x - __uint_as_float(hi));
 }
 
+// 2-instruction split for the activation operands: hi = x with the low 13 mantissa bits cleared (exactly what the tensor
+// core would read anyway), lo = x - hi (exact) passed as raw FP32 bits (the tensor core ignores its low 13 bits).
+// Measured with fbp_tc_selftest variant 24: 2.8e-7 of |A||W| (5-instruction rounded split: 9.5e-8).
+__device__ __forceinline__ void tf32_split_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 // ---- tcgen05 wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {       // one full warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
@@ -408,6 +416,249 @@ __global__ void __launch_bounds__(128 * NWG, 1) tc_forward_kernel(FastArgs a) {
         __syncthreads();
         float* dst = a.pair_out + (int64_t)(first + t0) * C;
         for (int i = tid; i < cnt * C; i += NT) dst[i] = outN[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);
+}
+
+
+// =====================================================================================================
+// forward, software-pipelined variant (opt-in: FBP_TC_FWD=2; not yet validated on hardware)
+// =====================================================================================================
+// The bring-up breakdown (profiles/r1f_tc_bringup.md) shows the first kernel paying the tensor-core time and ~0.85 ms of
+// latency serially because only one tile fits tensor memory.  Here the CTA still owns one tile's worth of TMEM, but the
+// phases of consecutive tiles are interleaved:
+//     wait MMA(t)  ->  layer 0 of tile t+1 -> A   ->  read D(t) into registers  ->  barrier  ->  issue MMA(t+1)
+//                  ->  epilogue math of tile t (tanh jets, cache, output dot, window) while MMA(t+1) runs
+// A is free once MMA(t) is complete and D is free once every thread holds its accumulators, so MMA(t+1) overlaps the
+// whole epilogue of tile t.  Two CTA-wide barriers per tile instead of three (the staged output copy is private to
+// warpgroup 0), the 2-instruction TF32 split, 4 warpgroups.
+template <class CF>
+__global__ void __launch_bounds__(512, 1) tc_forward_kernel2(FastArgs a) {
+    static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");
+    static_assert(3 * CF::C * 32 <= (int)TMEM_COLS, "A hi, A lo and D must fit the 512 TMEM columns");
+    constexpr int NWG = 4, NT = 512;
+    constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
+    constexpr uint32_t COL_AHI = 0, COL_ALO = C * 32, COL_D = 2 * C * 32;
+    using L = FwdSmem<CF, NWG>;
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ uint32_t tmem_slot;
+    float* bhi = sm + L::OFF_BHI;
+    float* blo = sm + L::OFF_BLO;
+    float* exch = sm + L::OFF_EXCH;
+    float* outN = sm + L::OFF_OUT;
+
+    const int tid = threadIdx.x, warp = warp_uniform();
+    const int g = tid >> 7, r = tid & 127;
+    const int jb = 8 * g;                   // this thread's 8 hidden units
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+
+    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
+    const int im = a.sub_ids[sp];
+    const int xd = a.xd;
+    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < xd) {
+            const float lo = ss[d], hi = ss[xd + d];
+            mu[d] = (hi + lo) * 0.5f;
+            isd[d] = 1.0f / ((hi - lo) * 0.5f);
+        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
+    }
+    const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
+    const float* prow = a.params + (int64_t)im * a.P;
+    fast_load_params<CF, NT>(sm, prow, xd, isd, a.axis, false);
+    stage_b(bhi, blo, prow + H * xd + H, H, 1, tid, NT);
+    if (tid == 0) {
+        mbar_init(&mma_bar[0], 1);
+        mbar_init(&mma_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const uint64_t bdesc_hi = make_smem_desc(smem_u32(bhi), B_LBO, B_SBO);
+    const uint64_t bdesc_lo = make_smem_desc(smem_u32(blo), B_LBO, B_SBO);
+    const int ntiles = (count + TP - 1) / TP;
+
+    int pf_pt = 0;
+    float pf_x[3] = {0.0f, 0.0f, 0.0f};
+    auto load_idx = [&](int tt) {
+        const int t0n = tt * TP;
+        if (t0n < count) pf_pt = a.spair_point[first + t0n + (r < min(TP, count - t0n) ? r : 0)];
+    };
+    auto load_val = [&](int tt) {
+        if (tt * TP < count) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
+        }
+    };
+    auto normalise = [&](float (&z)[3]) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
+    };
+    // layer 0 + tanh jets of this thread's 8 units at z -> A (hi, lo) in tensor memory
+    auto layer0_to_tmem = [&](const float (&z)[3]) {
+        float hv[8][C];
+#pragma unroll
+        for (int q4 = 0; q4 < 2; ++q4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + jb + 4 * q4);
+            const float4 w1 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + H + jb + 4 * q4);
+            const float4 w2 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + 2 * H + jb + 4 * q4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sm + CF::SM_B0 + jb + 4 * q4);
+            float4 wd[NS > 0 ? NS : 1];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) wd[s] = *reinterpret_cast<const float4*>(sm + CF::SM_W0D + s * H + jb + 4 * q4);
+            const float w0a[4] = {w0.x, w0.y, w0.z, w0.w}, w1a[4] = {w1.x, w1.y, w1.z, w1.w};
+            const float w2a[4] = {w2.x, w2.y, w2.z, w2.w}, b0a[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float (&av)[C] = hv[4 * q4 + e];
+                av[0] = fmaf(w2a[e], z[2], fmaf(w1a[e], z[1], fmaf(w0a[e], z[0], b0a[e])));
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const float wv = e == 0 ? wd[s].x : (e == 1 ? wd[s].y : (e == 2 ? wd[s].z : wd[s].w));
+                    if (s < NA2) { av[1 + 2 * s] = wv; av[2 + 2 * s] = 0.0f; }
+                    else av[1 + 2 * NA2 + (s - NA2)] = wv;
+                }
+                fast_tanh_jets<CF>(av);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) tf32_split_fast(hv[e][c], hi[e], lo[e]);
+            tmem_st8(tbase + lane_base + COL_AHI + c * 32 + jb, hi);
+            tmem_st8(tbase + lane_base + COL_ALO + c * 32 + jb, lo);
+        }
+    };
+    auto issue_mma = [&]() {
+        if (warp == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        issue_gemm_half(tbase + COL_D + c * 32 + nh * 16, tbase + COL_AHI + c * 32, tbase + COL_ALO + c * 32,
+                                        bdesc_hi, bdesc_lo, nh);
+                    mma_commit(&mma_bar[nh]);
+                }
+            }
+            __syncwarp();
+        }
+    };
+
+    // ---- prologue: tile 0 into A, MMA(0) in flight; coordinates of tile 1 and the index of tile 2 on their way -----
+    float z_cur[3];
+    load_idx(0);
+    load_val(0);
+    normalise(z_cur);
+    load_idx(1);
+    load_val(1);
+    load_idx(2);
+    layer0_to_tmem(z_cur);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    issue_mma();
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int t0 = t * TP;
+        const int cnt = min(TP, count - t0);
+        const uint32_t parity = (uint32_t)(t & 1);
+        const bool more = t + 1 < ntiles;
+        float z_next[3];
+        normalise(z_next);                                        // pf_x holds the coordinates of tile t+1
+        load_val(t + 2);
+        load_idx(t + 3);
+
+        mbar_wait_or_trap(&mma_bar[1], parity);                  // every MMA of tile t is complete: A is free, D is final
+        tc_fence_after();
+        if (more) layer0_to_tmem(z_next);
+        uint32_t v[C][8];
+#pragma unroll
+        for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + COL_D + c * 32 + jb, v[c]);
+        tmem_wait_ld();
+        tmem_wait_st();
+        tc_fence_before();
+        __syncthreads();                                         // A(t+1) complete, D(t) held in registers everywhere
+        if (more) issue_mma();
+
+        // ---- epilogue math of tile t (the tensor core works on tile t+1 meanwhile) -----------------------------
+        float up[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) up[c] = 0.0f;
+        float* cb = nullptr;
+        int cntb = 0;
+        if (a.cache != nullptr && r < cnt) {
+            constexpr int TPB = CF::TPB;
+            const int off = t0 + r;
+            const int t0b = (off / TPB) * TPB;
+            cntb = min(TPB, count - t0b);
+            cb = a.cache + (int64_t)(first + t0b) * (H * C) + (off - t0b);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float acc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = __uint_as_float(v[c][e]);
+            acc[0] += sm[CF::SM_B1 + jb + e];
+            fast_tanh_jets<CF>(acc);
+            if (cb != nullptr) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) cb[((jb + e) * C + c) * cntb] = acc[c];
+            }
+            const float wl = sm[CF::SM_WL + jb + e];
+#pragma unroll
+            for (int c = 0; c < C; ++c) up[c] = fmaf(wl, acc[c], up[c]);
+        }
+        if (g > 0) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) exch[((g - 1) * C + c) * TP + r] = up[c];
+        }
+        __syncthreads();
+        if (g == 0) {
+            float u[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float sum = up[c];
+#pragma unroll
+                for (int gg = 1; gg < NWG; ++gg) sum += exch[((gg - 1) * C + c) * TP + r];
+                u[c] = un_sd * (sum + (c == 0 ? sm[CF::SM_BL] : 0.0f));
+            }
+            u[0] += un_mu;
+            float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
+            fast_window<CF>(z_cur, isd, xd, flag, a.axis, w, w1, w2);
+            float* o = outN + r * C;
+            o[a.ext[0]] = u[0] * w;
+#pragma unroll
+            for (int s = 0; s < NA2; ++s) {
+                const float u1 = u[1 + 2 * s], u2 = u[2 + 2 * s];
+                o[a.ext[1 + 2 * s]] = u1 * w + u[0] * w1[s];
+                o[a.ext[2 + 2 * s]] = u2 * w + 2.0f * u1 * w1[s] + u[0] * w2[s];
+            }
+#pragma unroll
+            for (int s = 0; s < NA1; ++s) {
+                const int c = 1 + 2 * NA2 + s;
+                o[a.ext[c]] = u[c] * w + u[0] * w1[NA2 + s];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // warpgroup 0 only: the staged tile is complete
+            float* dst = a.pair_out + (int64_t)(first + t0) * C;
+            for (int i = r; i < cnt * C; i += 128) dst[i] = outN[i];
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // ... and copied before the next tile overwrites it
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) z_cur[d] = z_next[d];
     }
     tc_fence_before();
     __syncthreads();

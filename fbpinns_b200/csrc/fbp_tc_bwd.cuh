@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(BWD_NT, 1) tc_backward_kernel(FastArgs a) {
                 for (int c = 0; c < C; ++c) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) tf32_split(hv[e][c], hi[e], lo[e]);
+                    for (int e = 0; e < 8; ++e) tf32_split_fast(hv[e][c], hi[e], lo[e]);
                     tmem_st8(tbase + lane_base + COL_AHI + c * 32 + jb, hi);
                     tmem_st8(tbase + lane_base + COL_ALO + c * 32 + jb, lo);
                 }
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(BWD_NT, 1) tc_backward_kernel(FastArgs a) {
                 for (int c = 0; c < C; ++c) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) tf32_split(ab[e][c], hi[e], lo[e]);
+                    for (int e = 0; e < 8; ++e) tf32_split_fast(ab[e][c], hi[e], lo[e]);
                     tmem_st8(tbase + lane_base + COL_AHI + c * 32 + jb, hi);
                     tmem_st8(tbase + lane_base + COL_ALO + c * 32 + jb, lo);
                 }

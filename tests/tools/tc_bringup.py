@@ -52,8 +52,8 @@ def run(tag, kw, reps, breakdown):
             ts.append(a.elapsed_time(b))
         return round(float(np.mean(ts)), 4)
 
-    def outputs(kernel, nwg):
-        os.environ["FBP_TC_NWG"], os.environ["FBP_TC_DEBUG"] = str(nwg), "0"
+    def outputs(kernel, nwg, fwd=1):
+        os.environ["FBP_TC_NWG"], os.environ["FBP_TC_DEBUG"], os.environ["FBP_TC_FWD"] = str(nwg), "0", str(fwd)
         ev.plan.set_kernel(kernel)
         assert ev.plan.kernel == kernel, f"plan fell back to {ev.plan.kernel}"
         ev.pair_out.fill_(float("nan"))
@@ -82,6 +82,16 @@ def run(tag, kw, reps, breakdown):
                 res[f"{tag}_nwg{nwg}_dbg{dbg}_nocache_ms"] = timed(False)
             os.environ["FBP_TC_DEBUG"] = "0"
             print(json.dumps(res), flush=True)
+    # software-pipelined variant (FBP_TC_FWD=2)
+    got = outputs("tensor", 4, fwd=2)
+    res[f"{tag}_v2_nan"] = int(torch.isnan(got[0]).sum().item())
+    res[f"{tag}_v2_pair_out_rel"] = rel(got[0], ref[0])
+    if ref[1] is not None:
+        res[f"{tag}_v2_cache_rel"] = rel(got[1], ref[1])
+    res[f"{tag}_v2_ms"] = timed()
+    res[f"{tag}_v2_nocache_ms"] = timed(False)
+    os.environ["FBP_TC_FWD"] = "1"
+    print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":
