@@ -20,7 +20,8 @@
 // overlaps the latency-bound TMEM / MMA / epilogue chain of the next tile instead of alternating with it.
 //
 // No activation cache: the tensor core recomputes a2 faster than HBM delivers it.
-// Status: written after round 1's GPU budget was spent; enabled with FBP_TC_BWD=1 for bring-up in round 2.
+// Status: gradients validated on a B200 against the tiled kernel (3.6e-7, profiles/r1f_tc_bringup.md) on a small case
+// through the C ABI; not yet timed, hence opt-in (fbp_plan_set_kernel mode 4 / kernel="tensor-full").
 #pragma once
 #include "fbp_tc.cuh"
 
