@@ -337,7 +337,8 @@ def run_ours(args):
                        if not args.small else "SMALL cfg5 16x16 subdomains 256x256 grid (debug)",
                        "layers": list(layer_sizes), "subdomains": m, "points": n_points_global,
                        "pairs_this_rank": s_local, "parallelism": f"subdomain-slabs x{world}" if world > 1 else "single GPU",
-                       "cuda_graph": tr.update.graph is not None, "kernel_family": {"generic": "generic", "tiled": "tiled", "tensor": "tensor forward (tcgen05 3xTF32) + tiled reverse"}[ev.plan.forward_family],
+                       "cuda_graph": tr.update.graph is not None, "kernel_family": ("tensor forward + tensor reverse (tcgen05 3xTF32, weight gradient on FFMA2)" if ev.plan.kernel == "tensor-full" else
+                                         {"generic": "generic", "tiled": "tiled", "tensor": "tensor forward (tcgen05 3xTF32) + tiled reverse"}[ev.plan.forward_family]),
                        "l2": "per-step working set (pair jets 175 MB + indices 105 MB) exceeds the 126 MB L2; "
                              "per-kernel timings flush L2 with a 256 MB write between launches"},
             "ujs_point_evals_per_sec": int(tr.x_batch_global.shape[0]) * steps_per_s,
@@ -347,7 +348,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "fp32_fma", "kernel": "fast_backward_kernel", "achieved": bwd_tf, "peak": fma_peak,
+            "roofline": {"bound": "fp32_fma", "kernel": "tc_backward_kernel" if ev.plan.kernel == "tensor-full" else "fast_backward_kernel",
+                         "achieved": bwd_tf, "peak": fma_peak,
                          "unit": "TFLOP/s", "frac": bwd_tf / fma_peak if fma_peak else None,
                          "peak_source": "max of the FFMA and FFMA2 (fma.rn.f32x2) micro-benchmarks on this GPU (fbp_fma_peak / "
                                         "fbp_ffma2_peak); MEASURED_PEAKS.json holds only HBM / bf16-tensor peaks",

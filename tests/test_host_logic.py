@@ -199,6 +199,34 @@ def test_every_baseline_config_has_a_tiled_kernel_instance():
     assert not Plan([2, 32, 32, 32, 1], JetSpec(((0, ()),), 2, 1)).is_fast
 
 
+def test_tensor_family_selection(monkeypatch):
+    """which plans get the tcgen05 family: only H = 32 with two hidden layers and C <= 5; `auto` picks it for the instance
+    validated on hardware (cfg 5's jets) unless FBP_TC_AUTO=0; asking for it on other plans falls back to auto"""
+    from fbpinns_b200.engine import Plan
+    poisson = JetSpec(((0, (0, 0)), (0, (1, 1))), 2, 1)
+    monkeypatch.delenv("FBP_TC_AUTO", raising=False)
+    p = Plan([2, 32, 32, 1], poisson)
+    assert p.has_tensor and p.kernel == "auto" and p.forward_family == "tensor" and p.cache_per_pair == 32 * 5
+    p.set_kernel("tiled")
+    assert p.forward_family == "tiled"
+    p.set_kernel("tensor-full")
+    assert p.kernel == "tensor-full" and p.forward_family == "tensor" and p.cache_per_pair == 0      # recomputes, no cache
+    monkeypatch.setenv("FBP_TC_AUTO", "0")
+    assert Plan([2, 32, 32, 1], poisson).forward_family == "tiled"
+    monkeypatch.delenv("FBP_TC_AUTO")
+    # other jets of the same network: instance exists, but auto stays tiled until validated
+    ho = Plan([1, 32, 32, 1], JetSpec(((0, ()), (0, (0,)), (0, (0, 0))), 1, 1))
+    assert ho.has_tensor and ho.forward_family == "tiled"
+    ho.set_kernel("tensor")
+    assert ho.kernel == "tensor" and ho.forward_family == "tensor"
+    for ls, jet in (([2, 64, 64, 1], poisson), ([2, 32, 1], poisson), ([2, 16, 1], poisson),
+                    ([3, 32, 32, 1], JetSpec(((0, (0, 0)), (0, (1, 1)), (0, (2, 2))), 3, 1))):       # C = 7 does not fit TMEM
+        q = Plan(ls, jet)
+        assert not q.has_tensor and q.forward_family == "tiled"
+        q.set_kernel("tensor-full")
+        assert q.kernel == "auto" and q.forward_family == "tiled"
+
+
 def test_affine_constraining_fast_path_matches_generic():
     "A(x) u + B(x) detection + Leibniz on static coefficient jets == nested-jvp path (values and reverse mode)"
     from fbpinns_b200.jets import AffineConstraining
