@@ -58,10 +58,20 @@ def rel(a, b):
     return float(np.nanmax(np.abs(a - b)) / max(np.abs(b).max(), 1e-30))
 
 
-def main():
+SPECS = {   # name -> (xd, jet components as (k, l) pairs in JetSpec order)
+    "cfg5": (2, [(-1, -1), (0, -1), (1, -1), (0, 0), (1, 1)]),
+    "cfg2": (1, [(-1, -1), (0, -1), (0, 0)]),
+    "burgers": (2, [(-1, -1), (0, -1), (1, -1), (0, 0)]),
+    "value": (2, [(-1, -1)]),
+    "first": (2, [(-1, -1), (0, -1)]),
+}
+
+
+def main(spec="cfg5"):
     lib = _lib.load()
     rng = np.random.default_rng(0)
-    H, xd, Cj = 32, 2, 5
+    xd, comps = SPECS[spec]
+    H, Cj = 32, len(comps)
     P = H * xd + H + H * H + H + H + 1
     counts = [300, 128, 77, 1, 515]
     m, s = len(counts), sum(counts)
@@ -95,7 +105,7 @@ def main():
     for i, v in enumerate([xd, H, H, 1]):
         pd.layer_sizes[i] = v
     pd.activation, pd.window, pd.n_comp = 0, 0, Cj
-    for c, (k, l) in enumerate([(-1, -1), (0, -1), (1, -1), (0, 0), (1, 1)]):
+    for c, (k, l) in enumerate(comps):
         pd.comp_k[c], pd.comp_l[c] = k, l
     plan = C.c_void_p()
     _lib.check(lib.fbp_plan_create(C.byref(plan), C.byref(pd)), "fbp_plan_create")
@@ -103,7 +113,7 @@ def main():
     lines = []
 
     def emit(**kw):
-        line = json.dumps(kw)
+        line = json.dumps(dict(spec=spec, **kw))
         print(line, flush=True)
         lines.append(line)
         outdir = os.path.join(ROOT, "gpurun_out")
@@ -146,4 +156,9 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    for name in (sys.argv[1:] or ["cfg5"]):
+        if name == "all":
+            for n in SPECS:
+                main(n)
+        else:
+            main(name)
