@@ -243,7 +243,12 @@ class FBPINNTrainer(_Trainer):
         if not issubclass(decomposition, decompositions.RectangularDecompositionND):
             raise NotImplementedError(f"{decomposition} is not implemented by the B200 kernels "
                                       f"(RectangularDecompositionND family with the cosine window only)")
-        rng = np.random.default_rng(c.seed)
+        if getattr(c, "init_prng", "numpy") == "jax":
+            # the reference's key derivation (fbpinns/trainers.py:583, 603-605) on the restated threefry generator
+            from .util import jax_prng
+            rng = jax_prng.PRNGKey(c.seed)
+        else:
+            rng = np.random.default_rng(c.seed)
         ps_ = network.init_params_batched(rng, m, **c.network_init_kwargs)
         if ps_[0]:
             all_params["static"]["network"] = {"subdomain": ps_[0]}

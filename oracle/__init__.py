@@ -23,5 +23,6 @@ Pinning status (see DESIGN.md §"Oracle"):
     ordering == row-major nonzero of the dense inside mask) is restated as a test;
   * optax's Adam and jax.random's threefry are third-party code absent from the reference tree:
     Adam is restated from its published formula ("parity unpinned" for Adam bit patterns), and
-    parameter initialisation is always an explicit input.
+    parameter initialisation is always an explicit input (fbpinns_b200/util/jax_prng.py restates the threefry
+    generator and is pinned by its known-answer vectors only).
 """

@@ -282,3 +282,26 @@ def test_umma_descriptors_match_cute(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_jax_prng_known_answers():
+    """util/jax_prng.py (restated jax.random threefry): the three Threefry-2x32 known-answer vectors of the Random123
+    reference implementation (the ones JAX's own test-suite checks), two widely published JAX outputs, and the
+    consistency of the batched (vmap-like) initialisation with the per-key one."""
+    from fbpinns_b200.util import jax_prng as J
+    from fbpinns_b200.networks import FCN
+    hx = lambda r: tuple(int(v) for v in r)
+    assert hx(J.threefry_2x32(np.uint32([0, 0]), np.uint32([0, 0]))) == (0x6b200159, 0x99ba4efe)
+    m = 0xffffffff
+    assert hx(J.threefry_2x32(np.uint32([m, m]), np.uint32([m, m]))) == (0x1cb996fc, 0xbb002be7)
+    assert hx(J.threefry_2x32(np.uint32([0x13198a2e, 0x03707344]), np.uint32([0x243f6a88, 0x85a308d3]))) == (0xc4923a9c, 0x483df7a0)
+    assert J.split(J.PRNGKey(0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+    assert J.uniform(J.PRNGKey(0)) == np.float32(0.41845703)
+    root = J.PRNGKey(3)
+    _, batched = FCN.init_params_batched(root, 5, [2, 16, 1])
+    subkeys = J.split(root, 6)[1:]
+    for i in range(5):
+        _, single = FCN.init_params(subkeys[i], [2, 16, 1])
+        for (W, B), (w, b) in zip(batched["layers"], single["layers"]):
+            assert torch.equal(W[i], w) and torch.equal(B[i], b)
+            assert float(w.abs().max()) <= 1 / np.sqrt(w.shape[1]) and w.dtype == torch.float32
