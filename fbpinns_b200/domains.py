@@ -6,6 +6,7 @@ import numpy as np
 import scipy.stats
 import torch
 
+from .util import jax_prng
 
 class Domain:
     """Base domain class (fbpinns/domains.py:18-55)."""
@@ -91,6 +92,8 @@ class RectangularDomainND(Domain):
                 s = scipy.stats.qmc.Halton(xd).random(n)
             elif sampler == "sobol":
                 s = scipy.stats.qmc.Sobol(xd).random(n)
+            elif jax_prng.is_key(key):
+                s = jax_prng.uniform(key, (n, xd)).astype(np.float64)      # jax.random.uniform(key, (n, xd)), restated
             else:
                 rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(key)
                 s = rng.random((n, xd))
