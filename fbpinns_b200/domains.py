@@ -8,6 +8,7 @@ import torch
 
 from .util import jax_prng
 
+
 class Domain:
     """Base domain class (fbpinns/domains.py:18-55)."""
 
