@@ -28,6 +28,7 @@ from .util import jax_prng      # noqa: E402  numpy restatement of jax.random's 
 
 class FCN(Network):
     "Fully connected network"
+    ACTIVATION = "tanh"
 
     @staticmethod
     def init_params(key, layer_sizes):
@@ -82,6 +83,124 @@ class FCN(Network):
     def network_fn(params, x):
         "Host mirror for a SINGLE point (xd,) and a single subdomain's parameters (fbpinns/networks.py:61-68)"
         layers = params["trainable"]["network"]["subdomain"]["layers"]
+        for w, b in layers[:-1]:
+            x = torch.tanh(w @ x + b)
+        w, b = layers[-1]
+        return w @ x + b
+
+
+def _layers_from_subkeys(subkeys, layer_sizes, gain, n_extra):
+    "row i: the layers `init_params(subkeys[i], layer_sizes)` of the reference draws (split per layer, then w_key / b_key)"
+    layers = []
+    layer_keys = jax_prng.split_batched(subkeys, len(layer_sizes) - 1)
+    for l, (fi, fo) in enumerate(zip(layer_sizes[:-1], layer_sizes[1:])):
+        wb = jax_prng.split_batched(layer_keys[:, l], 2)
+        v = np.float32(np.sqrt(np.float32(gain / fi)))
+        w = torch.from_numpy(jax_prng.uniform_batched(wb[:, 0], (fo, fi), -v, v))
+        b = torch.from_numpy(jax_prng.uniform_batched(wb[:, 1], (fo,), -v, v))
+        layers.append((w, b) + tuple(torch.ones_like(b) for _ in range(n_extra)))
+    return layers
+
+
+def _layers_batched(key, m, layer_sizes, gain, n_extra):
+    """m independent stacks of (W (m,out,in), b (m,out), n_extra x ones (m,out)) with W, b ~ U(-v, v), v = sqrt(gain/in):
+    the draws of every reference network's `_random_layer_params`, for a numpy Generator / seed or a threefry ROOT key
+    (then `key, *subkeys = split(key, m+1)` as at fbpinns/trainers.py:603)."""
+    if jax_prng.is_key(key):
+        return _layers_from_subkeys(jax_prng.split(key, m + 1)[1:], layer_sizes, gain, n_extra)
+    rng = _rng(key)
+    layers = []
+    for fi, fo in zip(layer_sizes[:-1], layer_sizes[1:]):
+        v = np.sqrt(gain / fi)
+        w = torch.tensor(rng.uniform(-v, v, size=(m, fo, fi)), dtype=torch.float32)
+        b = torch.tensor(rng.uniform(-v, v, size=(m, fo)), dtype=torch.float32)
+        layers.append((w, b) + tuple(torch.ones_like(b) for _ in range(n_extra)))
+    return layers
+
+
+def _single(layers_batched):
+    return [tuple(t[0] for t in leaf) for leaf in layers_batched]
+
+
+class AdaptiveFCN(Network):
+    "Fully connected network with adaptive activations a * tanh(x / a), a per unit (fbpinns/networks.py:70-101)"
+    ACTIVATION, N_EXTRA, GAIN = "adaptive_tanh", 1, 1.0
+
+    @classmethod
+    def init_params(cls, key, layer_sizes):
+        if jax_prng.is_key(key):          # a single network draws from its own key: no subdomain split
+            return {}, {"layers": _single(_layers_from_subkeys(key[None], layer_sizes, cls.GAIN, cls.N_EXTRA))}
+        return {}, {"layers": _single(_layers_batched(key, 1, layer_sizes, cls.GAIN, cls.N_EXTRA))}
+
+    @classmethod
+    def init_params_batched(cls, key, m, layer_sizes):
+        return {}, {"layers": _layers_batched(key, m, layer_sizes, cls.GAIN, cls.N_EXTRA)}
+
+    @staticmethod
+    def network_fn(params, x):
+        layers = params["trainable"]["network"]["subdomain"]["layers"]
+        for w, b, a in layers[:-1]:
+            x = a * torch.tanh((w @ x + b) / a)
+        w, b, _ = layers[-1]
+        return w @ x + b
+
+
+class SIREN(AdaptiveFCN):
+    "Fully connected network with sin activations, U(+-sqrt(6/in)) initialisation (fbpinns/networks.py:103-133)"
+    ACTIVATION, N_EXTRA, GAIN = "sin", 0, 6.0
+
+    @staticmethod
+    def network_fn(params, x):
+        layers = params["trainable"]["network"]["subdomain"]["layers"]
+        for w, b in layers[:-1]:
+            x = torch.sin(w @ x + b)
+        w, b = layers[-1]
+        return w @ x + b
+
+
+class AdaptiveSIREN(AdaptiveFCN):
+    "Fully connected network with adaptive sin activations c * sin(o * x), c and o per unit (fbpinns/networks.py:135-166)"
+    ACTIVATION, N_EXTRA, GAIN = "adaptive_sin", 2, 6.0
+
+    @staticmethod
+    def network_fn(params, x):
+        layers = params["trainable"]["network"]["subdomain"]["layers"]
+        for w, b, c, o in layers[:-1]:
+            x = c * torch.sin(o * (w @ x + b))
+        w, b, _, _ = layers[-1]
+        return w @ x + b
+
+
+class FourierFCN(FCN):
+    """FCN on Fourier features [sin(omega x), cos(omega x)] with a static omega per subdomain,
+    omega = 2 pi (mu + sd N(0,1)) of shape (n_features, xd)  (fbpinns/networks.py:168-194)"""
+    ACTIVATION = "fourier_tanh"
+
+    @staticmethod
+    def _omega(key, m, xd, mu, sd, n_features):
+        if jax_prng.is_key(key):
+            raise NotImplementedError("threefry initialisation of FourierFCN (needs XLA's float32 erf_inv bits)")
+        rng = _rng(key)
+        return torch.tensor(2 * np.pi * (mu + sd * rng.standard_normal((m, n_features, xd))), dtype=torch.float32)
+
+    @staticmethod
+    def init_params(key, layer_sizes, mu, sd, n_features):
+        st, tr = FourierFCN.init_params_batched(key, 1, layer_sizes, mu, sd, n_features)
+        return {"omega": st["omega"][0]}, {"layers": _single(tr["layers"])}
+
+    @staticmethod
+    def init_params_batched(key, m, layer_sizes, mu, sd, n_features):
+        rng = _rng(key)
+        omega = FourierFCN._omega(rng, m, layer_sizes[0], mu, sd, n_features)
+        sizes = [2 * n_features] + list(layer_sizes)[1:]
+        return {"omega": omega}, {"layers": _layers_batched(rng, m, sizes, 1.0, 0)}
+
+    @staticmethod
+    def network_fn(params, x):
+        omega = params["static"]["network"]["subdomain"]["omega"]
+        layers = params["trainable"]["network"]["subdomain"]["layers"]
+        x = omega @ x
+        x = torch.cat([torch.sin(x), torch.cos(x)])
         for w, b in layers[:-1]:
             x = torch.tanh(w @ x + b)
         w, b = layers[-1]

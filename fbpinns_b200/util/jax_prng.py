@@ -101,5 +101,14 @@ def uniform_batched(keys, shape, minval, maxval):
     return np.maximum(minval, (f * (maxval - minval) + minval).astype(np.float32)).reshape((len(keys),) + tuple(shape))
 
 
+def normal(key, shape=()):
+    """jax.random.normal for float32: sqrt(2) * erfinv(u), u uniform on (nextafter(-1, 0), 1).  XLA's float32 erf_inv
+    polynomial is replaced by scipy's float64 erfinv rounded to float32 (agrees to float32 rounding, not bit for bit)."""
+    from scipy.special import erfinv
+    lo = np.nextafter(np.float32(-1.0), np.float32(0.0))
+    u = uniform(key, shape, lo, np.float32(1.0))
+    return (np.sqrt(2.0) * erfinv(u.astype(np.float64))).astype(np.float32)
+
+
 def is_key(key):
     return isinstance(key, np.ndarray) and key.dtype == np.uint32 and key.shape == (2,)

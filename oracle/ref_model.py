@@ -71,16 +71,40 @@ def cosine_window(xmin, xmax, x):
     return torch.prod(ws, dim=1, keepdim=True)
 
 
-def model_inner(ps_take, layers_take, x_take):
+def network_forward(network, layers_take, h, static_take=None):
+    """Network.network_fn of the reference, batched over the leading (pair) axis: every leaf of `layers_take` carries the
+    pair's own parameters.  network: "fcn" (fbpinns/networks.py:61-68), "adaptive_fcn" (:93-101), "siren" (:125-133),
+    "adaptive_siren" (:158-166), "fourier" (:183-194, static_take = {"omega": (s, n_features, xd)})."""
+    mv = lambda w, v: torch.einsum("soi,si->so", w, v)
+    if network == "fourier":
+        h = mv(static_take["omega"], h)
+        h = torch.cat([torch.sin(h), torch.cos(h)], dim=1)
+        network = "fcn"
+    if network == "fcn":
+        for w, b in layers_take[:-1]:
+            h = torch.tanh(mv(w, h) + b)
+    elif network == "adaptive_fcn":
+        for w, b, a in layers_take[:-1]:
+            h = a * torch.tanh((mv(w, h) + b) / a)
+    elif network == "siren":
+        for w, b in layers_take[:-1]:
+            h = torch.sin(mv(w, h) + b)
+    elif network == "adaptive_siren":
+        for w, b, c, o in layers_take[:-1]:
+            h = c * torch.sin(o * (mv(w, h) + b))
+    else:
+        raise ValueError(f"unknown network {network}")
+    w, b = layers_take[-1][0], layers_take[-1][1]
+    return mv(w, h) + b
+
+
+def model_inner(ps_take, layers_take, x_take, network="fcn", static_take=None):
     """FBPINN_model_inner (fbpinns/trainers.py:113-118) for a batch of pairs.
     ps_take = [xmins, xmaxs, wmins, wmaxs, flags, unnorms] gathered per pair."""
     xmin, xmax = ps_take[0], ps_take[1]
     mu, sd = (xmax + xmin) / 2, (xmax - xmin) / 2
     h = (x_take - mu) / sd                                           # norm_fn, decompositions.py:183-188
-    for w, b in layers_take[:-1]:                                   # FCN.network_fn, networks.py:61-68
-        h = torch.tanh(torch.einsum("soi,si->so", w, h) + b)
-    w, b = layers_take[-1]
-    u_raw = torch.einsum("soi,si->so", w, h) + b
+    u_raw = network_forward(network, layers_take, h, static_take)   # Network.network_fn
     un = ps_take[5]
     u = u_raw * un[:, 1:2] + un[:, 0:1]                             # unnorm_fn, decompositions.py:190-194
     flag = ps_take[4]
@@ -88,7 +112,8 @@ def model_inner(ps_take, layers_take, x_take):
     return u * win, win, u_raw
 
 
-def fbpinn_model(decomp_cut, layers_cut, x_batch, takes, constraining_fn=None, all_params=None):
+def fbpinn_model(decomp_cut, layers_cut, x_batch, takes, constraining_fn=None, all_params=None, network="fcn",
+                 net_static_cut=None):
     """FBPINN_model (fbpinns/trainers.py:126-177).  decomp_cut / layers_cut are already cut to all_ims
     order (static_params = cut_all(...), trainable = concat(active, fixed))."""
     m_take, n_take, p_take, np_take, npou = takes
@@ -96,8 +121,9 @@ def fbpinn_model(decomp_cut, layers_cut, x_batch, takes, constraining_fn=None, a
                                        for t in (m_take, n_take, p_take, np_take)]
     x_take = x_batch[n_take]
     ps_take = [p[m_take] for p in decomp_cut["subdomain"]["params"]]
-    layers_take = [(w[m_take], b[m_take]) for w, b in layers_cut]
-    us, ws, us_raw = model_inner(ps_take, layers_take, x_take)
+    layers_take = [tuple(t[m_take] for t in leaf) for leaf in layers_cut]
+    static_take = None if net_static_cut is None else {k: v[m_take] for k, v in net_static_cut.items()}
+    us, ws, us_raw = model_inner(ps_take, layers_take, x_take, network, static_take)
 
     cat = torch.cat([us, ws], dim=1)
     seg = torch.zeros((len(np_take), cat.shape[1]), dtype=cat.dtype).index_add(0, p_take, cat)
@@ -133,24 +159,25 @@ def get_ujs(x_batch, jmaps, u_fn):
     return [jacs[il][io][:, iu:iu + 1] for il, io, iu in jac_is]
 
 
-def fbpinn_forward(decomp_cut, layers_cut, x_batch, takes, jmaps, constraining_fn=None, all_params=None):
+def fbpinn_forward(decomp_cut, layers_cut, x_batch, takes, jmaps, constraining_fn=None, all_params=None, network="fcn",
+                   net_static_cut=None):
     """FBPINN_forward, fbpinns/trainers.py:197-203."""
     def u_fn(xb):
-        return fbpinn_model(decomp_cut, layers_cut, xb, takes, constraining_fn, all_params)[0], ()
+        return fbpinn_model(decomp_cut, layers_cut, xb, takes, constraining_fn, all_params, network, net_static_cut)[0], ()
     return get_ujs(x_batch, jmaps, u_fn)
 
 
 def fbpinn_loss(active_layers, fixed_layers, decomp_cut, takess, constraints, jmapss, loss_fn,
-                constraining_fn=None, make_all_params=None):
+                constraining_fn=None, make_all_params=None, network="fcn", net_static_cut=None):
     """FBPINN_loss, fbpinns/trainers.py:249-267.
     make_all_params(layers_cut) builds whatever `all_params` object loss_fn / constraining_fn expect."""
-    layers_cut = [(torch.cat([wa, wf], 0), torch.cat([ba, bf], 0))
-                  for (wa, ba), (wf, bf) in zip(active_layers, fixed_layers)]
+    layers_cut = [tuple(torch.cat([ta, tf], 0) for ta, tf in zip(la, lf)) for la, lf in zip(active_layers, fixed_layers)]
     all_params = make_all_params(layers_cut) if make_all_params is not None else None
     out = []
     for takes, jmaps, constraint in zip(takess, jmapss, constraints):
         x_batch = constraint[0]
-        ujs = fbpinn_forward(decomp_cut, layers_cut, x_batch, takes, jmaps, constraining_fn, all_params)
+        ujs = fbpinn_forward(decomp_cut, layers_cut, x_batch, takes, jmaps, constraining_fn, all_params, network,
+                             net_static_cut)
         out.append(list(constraint) + ujs)
     return loss_fn(all_params, out)
 
@@ -176,7 +203,7 @@ def cut_decomp(decomp_t, ims):
 
 def cut_layers(layers, ims):
     ims = torch.as_tensor(np.asarray(ims), dtype=torch.long)
-    return [(w[ims], b[ims]) for w, b in layers]
+    return [tuple(t[ims] for t in leaf) for leaf in layers]
 
 
 def init_fcn_params(rng, m, layer_sizes, dtype=np.float32):

@@ -257,3 +257,26 @@ def test_oracle_parameter_gradients_match_finite_differences_of_reference(name):
         idx = tuple(int(v) for v in pick[2:2 + gt.dim()])
         got = float(gt[idx]) if gt is not None else 0.0
         assert abs(got - fd) <= 1e-6 * max(1.0, abs(fd)) + 1e-7 * float(np.abs(g["grad_fd"]).max()), (name, pick, got, fd)
+
+
+def test_network_plugins_match_reference_source():
+    """FCN / AdaptiveFCN / SIREN / AdaptiveSIREN / FourierFCN: the host mirrors (fbpinns_b200/networks.py, single point)
+    and the oracle's pair-batched network_forward reproduce the outputs of the reference's own `network_fn`s
+    (tests/golden/refnetworks.npz, made by make_golden_networks.py from fbpinns/networks.py:61-194 under the shim)."""
+    from fbpinns_b200 import networks as N
+    from oracle import ref_model
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refnetworks.npz"))
+    x = torch.tensor(g["x"])
+    for name, cls, n_extra in [("fcn", N.FCN, 0), ("adaptive_fcn", N.AdaptiveFCN, 1), ("siren", N.SIREN, 0),
+                               ("adaptive_siren", N.AdaptiveSIREN, 2), ("fourier", N.FourierFCN, 0)]:
+        layers = [tuple(torch.tensor(g[f"{name}_l{l}_{i}"]) for i in range(2 + n_extra)) for l in range(3)]
+        st = {"network": {"subdomain": {"omega": torch.tensor(g["fourier_omega"])}}} if name == "fourier" else {}
+        params = {"static": st, "trainable": {"network": {"subdomain": {"layers": layers}}}}
+        y = torch.stack([cls.network_fn(params, xi) for xi in x]).numpy()
+        assert np.abs(y - g[f"{name}_y"]).max() < 1e-13, name
+        # oracle: every pair carries its own copy of the parameters
+        s = x.shape[0]
+        take = [tuple(t.unsqueeze(0).expand(s, *t.shape) for t in leaf) for leaf in layers]
+        stt = {"omega": torch.tensor(g["fourier_omega"]).unsqueeze(0).expand(s, -1, -1)} if name == "fourier" else None
+        yo = ref_model.network_forward(name, take, x, stt).numpy()
+        assert np.abs(yo - g[f"{name}_y"]).max() < 1e-13, name

@@ -195,3 +195,68 @@ def test_kernel_math_prototype_mixed_derivative():
     for l, (gW, gb) in enumerate(grads):
         assert common.rel_err(gW, gs[2 * l].numpy()) < 1e-9
         assert common.rel_err(gb, gs[2 * l + 1].numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_activation_jet_formulas_match_autograd(kind):
+    """proto_activation_math (the formulas of the generic kernels' activation variants: tanh, alpha*tanh(a/alpha), sin,
+    c*sin(o*a) — the reference's FCN / AdaptiveFCN / SIREN / AdaptiveSIREN, fbpinns/networks.py:61-166) against torch
+    autograd of the activation composed with a second-order Taylor path, forward jets and the full reverse pass
+    (pre-activation cotangents and the activation parameters' gradients), including a mixed second derivative."""
+    import proto_activation_math as pa
+    jet = JetSpec(((0, (0, 0)), (0, (0, 1)), (0, (1, 1))), 2, 1)
+    order = [len(p) for p in jet.comps]
+    i1 = [jet.index[(p[0],)] if len(p) == 2 else 0 for p in jet.comps]
+    i2 = [jet.index[(p[1],)] if len(p) == 2 else 0 for p in jet.comps]
+    rng = np.random.default_rng(kind)
+    B, C = 7, jet.C
+    a = rng.standard_normal((B, C))
+    hbar = rng.standard_normal((B, C))
+    p = tuple(rng.uniform(0.5, 1.5, B) for _ in range(pa.N_EXTRA[kind]))
+
+    def f(v, ps):
+        if kind == 0:
+            return torch.tanh(v)
+        if kind == 1:
+            return ps[0] * torch.tanh(v / ps[0])
+        if kind == 2:
+            return torch.sin(v)
+        return ps[0] * torch.sin(ps[1] * v)
+
+    h_ref = np.zeros((B, C))
+    ab_ref = np.zeros((B, C))
+    pb_ref = [np.zeros(B) for _ in p]
+    for s in range(B):
+        at = torch.tensor(a[s], dtype=torch.float64, requires_grad=True)
+        pt = [torch.tensor(q[s], dtype=torch.float64, requires_grad=True) for q in p]
+        tau = torch.zeros(2, dtype=torch.float64, requires_grad=True)
+        path = at[0]
+        for c, comp in enumerate(jet.comps):
+            if len(comp) == 1:
+                path = path + at[c] * tau[comp[0]]
+            elif len(comp) == 2:
+                path = path + (0.5 if comp[0] == comp[1] else 1.0) * at[c] * tau[comp[0]] * tau[comp[1]]
+        hv = f(path, pt)
+        g1, = torch.autograd.grad(hv, tau, create_graph=True)
+        hs = []
+        for c, comp in enumerate(jet.comps):
+            if len(comp) == 0:
+                hs.append(hv)
+            elif len(comp) == 1:
+                hs.append(g1[comp[0]])
+            else:
+                g2, = torch.autograd.grad(g1[comp[0]], tau, create_graph=True)
+                hs.append(g2[comp[1]])
+        hs = torch.stack(hs)
+        h_ref[s] = hs.detach().numpy()
+        L = (hs * torch.tensor(hbar[s])).sum()
+        grads = torch.autograd.grad(L, [at] + pt)
+        ab_ref[s] = grads[0].numpy()
+        for i in range(len(p)):
+            pb_ref[i][s] = grads[1 + i].item()
+    h = pa.act_forward(kind, a, p, order, i1, i2)
+    ab, pbar = pa.act_backward(kind, a, p, hbar, order, i1, i2)
+    assert np.allclose(h, h_ref, rtol=1e-10, atol=1e-10)
+    assert np.allclose(ab, ab_ref, rtol=1e-10, atol=1e-10)
+    for got, ref in zip(pbar, pb_ref):
+        assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
