@@ -62,6 +62,8 @@ SIGNATURES = {
     "fbp_plan_cache_per_pair": (_I64, [_P]),
     "fbp_pack_params": (C.c_int, [_P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _P]),
     "fbp_unpack_params": (C.c_int, [_P, _I64, _P, C.POINTER(_P), C.POINTER(_P), _P]),
+    "fbp_pack_extra": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _I32, _P]),
+    "fbp_plan_n_extra": (_I32, [_P]),
     "fbp_inside_count": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, _I32, _P, _P, _P]),
     "fbp_nonzero_i32": (C.c_int, [_P, _I64, _P, C.POINTER(_I64), _P]),
     "fbp_gather_rows": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),

@@ -20,15 +20,15 @@ def FBPINN_model(c, all_params, active, x_batch, device=None):
     dev = torch.device(device or c.device)
     dd = c.decomposition._device(all_params, dev)
     ud, xd = all_params["static"]["problem"]["dims"]
-    layer_sizes = list(c.network_init_kwargs["layer_sizes"])
+    from . import networks
+    activation, layer_sizes, layers = networks.kernel_layers(c.network, all_params, dev)
     x = x_batch.to(dev, torch.float32).contiguous()
     _, mc = dd.inside_count(x)
     _, a_ims, f_ims, all_ims, pos = active_set_algebra(np.asarray(active), mc.cpu().numpy())
-    plan = Plan(layer_sizes, JetSpec(tuple((iu, ()) for iu in range(ud)), xd, ud), kernel=getattr(c, "kernel", "auto"))
+    plan = Plan(layer_sizes, JetSpec(tuple((iu, ()) for iu in range(ud)), xd, ud), kernel=getattr(c, "kernel", "auto"),
+                activation=activation)
     takes = DeviceTakes(dd, x, pos, all_ims, len(a_ims), tile_points=plan.tile_points)
     ev = ConstraintEvaluator(plan, takes, x, dd, activation_cache=False)
-    layers = [(w.to(dev, torch.float32), b.to(dev, torch.float32))
-              for w, b in all_params["trainable"]["network"]["subdomain"]["layers"]]
     params = pack_params(plan, layers)
     with torch.no_grad():
         u = ev.forward(params)

@@ -51,7 +51,10 @@ int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
     FBP_REQUIRE(d->layer_sizes[0] == d->xd, "fbp_plan_create: layer_sizes[0]=%d must equal xd=%d", d->layer_sizes[0], d->xd);
     FBP_REQUIRE(d->layer_sizes[d->n_layers] == d->ud, "fbp_plan_create: last layer size %d must equal ud=%d",
                 d->layer_sizes[d->n_layers], d->ud);
-    FBP_REQUIRE(d->activation == FBP_ACT_TANH, "fbp_plan_create: activation %d not implemented (tanh only)", d->activation);
+    FBP_REQUIRE(d->activation >= FBP_ACT_TANH && d->activation <= FBP_ACT_FOURIER_TANH,
+                "fbp_plan_create: activation %d not implemented (FBP_ACT_* 0..4)", d->activation);
+    FBP_REQUIRE(d->activation != FBP_ACT_FOURIER_TANH || d->n_layers >= 2,
+                "fbp_plan_create: FBP_ACT_FOURIER_TANH needs the feature layer plus at least one more layer");
     FBP_REQUIRE(d->window == FBP_WINDOW_COSINE, "fbp_plan_create: window %d not implemented (cosine only)", d->window);
     FBP_REQUIRE(d->n_comp >= 1 && d->n_comp <= FBP_MAX_COMP, "fbp_plan_create: n_comp=%d unsupported (1..%d)", d->n_comp, FBP_MAX_COMP);
     FBP_REQUIRE(d->comp_k[0] < 0 && d->comp_l[0] < 0, "fbp_plan_create: component 0 must be the value");
@@ -66,9 +69,14 @@ int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
         if (d->layer_sizes[l] < 1) { delete p; FBP_REQUIRE(false, "fbp_plan_create: layer size must be >= 1"); }
         pd.size[l] = d->layer_sizes[l];
     }
+    pd.act = d->activation;
+    pd.n_extra = d->activation == FBP_ACT_ADAPTIVE_TANH ? 1 : (d->activation == FBP_ACT_ADAPTIVE_SIN ? 2 : 0);
     for (int l = 0; l < d->n_layers; ++l) {
         pd.woff[l] = off; off += pd.size[l] * pd.size[l + 1];
         pd.boff[l] = off; off += pd.size[l + 1];
+        for (int e = 0; e < pd.n_extra; ++e) { pd.eoff[l][e] = off; off += pd.size[l + 1]; }
+        pd.lkind[l] = d->activation == FBP_ACT_FOURIER_TANH ? (l == 0 ? FBP_ACT_SIN : FBP_ACT_TANH) : d->activation;
+        pd.lfrozen[l] = (d->activation == FBP_ACT_FOURIER_TANH && l == 0) ? 1 : 0;
         if (l < d->n_layers - 1) { pd.hid_off[l] = hoff; hoff += pd.size[l + 1]; }
     }
     pd.P = off;
@@ -95,7 +103,7 @@ int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
         if (f1 < 0 || f2 < 0) { delete p; FBP_REQUIRE(false, "fbp_plan_create: jet set not closed: order-2 component %d lacks its order-1 components", c); }
         pd.i1[c] = f1; pd.i2[c] = f2;
     }
-    p->fast_id = fbp_fast_lookup(d, &p->fast);
+    p->fast_id = d->activation == FBP_ACT_TANH ? fbp_fast_lookup(d, &p->fast) : -1;   // activation variants: generic family
     p->tc_ok = p->fast_id >= 0 && fbp_tc_supported(p->fast, p->dev.C) != 0;
     {   // instance validated on B200 (profiles/r1f_tc_bringup.md): two second-order axes, C = 5 (cfg 5)
         const char* e = getenv("FBP_TC_AUTO");
@@ -115,6 +123,7 @@ int64_t fbp_plan_param_count(const fbp_plan* plan) { return plan ? plan->dev.P :
 int32_t fbp_plan_is_fast(const fbp_plan* plan) { return plan && plan->fast_id >= 0 ? 1 : 0; }
 int32_t fbp_plan_tile_points(const fbp_plan* plan) { return (plan && plan->use_fast()) ? plan->fast.tile_points : 128; }
 
+int32_t fbp_plan_n_extra(const fbp_plan* plan) { return plan ? plan->dev.n_extra : -1; }
 int32_t fbp_plan_has_tensor(const fbp_plan* plan) { return plan && plan->fast_id >= 0 && plan->tc_ok ? 1 : 0; }
 int32_t fbp_plan_forward_family(const fbp_plan* plan) {
     if (!plan) return -1;
@@ -140,7 +149,8 @@ int64_t fbp_plan_cache_per_pair(const fbp_plan* plan) {
 
 int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan) {
     if (!plan) return -1;
-    return plan->use_fast() ? 0 : (int64_t)plan->dev.hid_total * plan->dev.C;
+    // the activation variants keep the pre-activation jets next to the activations
+    return plan->use_fast() ? 0 : (int64_t)plan->dev.hid_total * plan->dev.C * (plan->dev.act != FBP_ACT_TANH ? 2 : 1);
 }
 
 static int check_view(const fbp_takes_view* tv, const char* who) {
@@ -157,6 +167,9 @@ int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x
     if (int rc = check_view(tv, "fbp_forward")) return rc;
     if (plan->use_fast())
         return fbp_fast_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, d_act_cache, (cudaStream_t)stream);
+    if (plan->dev.act != FBP_ACT_TANH)
+        return fbp_generic_act_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, d_scratch, scratch_floats,
+                                       (cudaStream_t)stream);
     return fbp_generic_forward(plan, tv, d_x, d_params, d_sub_static, d_pair_out, d_scratch, scratch_floats, (cudaStream_t)stream);
 }
 
@@ -175,6 +188,9 @@ int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_
                                  (cudaStream_t)stream);
     FBP_REQUIRE((accumulate & ~FBP_BWD_ACCUMULATE) == 0,
                 "fbp_backward(generic): FBP_BWD_NO_REDUCE / FBP_BWD_REDUCE_ONLY need a tiled plan");
+    if (plan->dev.act != FBP_ACT_TANH)
+        return fbp_generic_act_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_scratch,
+                                        scratch_floats, (cudaStream_t)stream);
     return fbp_generic_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_scratch,
                                 scratch_floats, (cudaStream_t)stream);
 }

@@ -62,6 +62,12 @@ struct PlanDev {
     int i1[FBP_MAX_COMP];               // order 2: component index of d/dx_k
     int i2[FBP_MAX_COMP];               // order 2: component index of d/dx_l
     int ss;                             // floats per static subdomain record = 2*xd+3
+    // activation variants (generic family only; all zero for plain FCN plans)
+    int act;                            // FBP_ACT_*
+    int n_extra;                        // activation parameters per unit (0, 1, 2)
+    int lkind[FBP_MAX_LAYERS];          // per hidden layer: FBP_ACT_TANH / ADAPTIVE_TANH / SIN / ADAPTIVE_SIN
+    int lfrozen[FBP_MAX_LAYERS];        // 1: the layer's W, b get no gradient (Fourier feature layer)
+    int eoff[FBP_MAX_LAYERS][2];        // offsets of the layer's activation parameters inside a packed row
 };
 
 // Tiled ("fast") kernel family parameters, valid when fast_id >= 0.
@@ -157,6 +163,14 @@ int fbp_generic_forward(const fbp_plan* plan, const fbp_takes_view* tv, const fl
 int fbp_generic_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                          const float* d_sub_static, const float* d_grow, float* d_grads, int accumulate,
                          float* d_scratch, int64_t scratch_floats, cudaStream_t stream);
+
+// generic family, activation variants (fbp_generic_act.cu): plans with dev.act != FBP_ACT_TANH
+int fbp_generic_act_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
+                            const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats,
+                            cudaStream_t stream);
+int fbp_generic_act_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
+                             const float* d_sub_static, const float* d_grow, float* d_grads, int accumulate,
+                             float* d_scratch, int64_t scratch_floats, cudaStream_t stream);
 
 // tiled family: returns -1 if no instance matches
 int fbp_fast_lookup(const fbp_plan_desc* desc, FastSpec* spec);

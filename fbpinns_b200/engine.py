@@ -34,10 +34,16 @@ def device_info():
 class Plan:
     """Network shape + jet spec (the static arguments `model_fns`/`jmaps` of the reference's FBPINN_forward)."""
 
-    def __init__(self, layer_sizes, jet: JetSpec, kernel="auto"):
+    ACTIVATIONS = {"tanh": 0, "adaptive_tanh": 1, "sin": 2, "adaptive_sin": 3, "fourier_tanh": 4}
+
+    def __init__(self, layer_sizes, jet: JetSpec, kernel="auto", activation="tanh"):
+        """activation: the reference Network the packed rows belong to — "tanh" FCN, "adaptive_tanh" AdaptiveFCN, "sin"
+        SIREN, "adaptive_sin" AdaptiveSIREN, "fourier_tanh" FourierFCN (layer_sizes then starts [xd, 2*n_features, ...]
+        and layer 0 holds the static feature layer).  Everything but "tanh" runs on the generic kernel family."""
         lib = _lib.load()
         self.layer_sizes = [int(v) for v in layer_sizes]
         self.jet = jet
+        self.activation = activation
         if len(self.layer_sizes) - 1 > _lib.FBP_MAX_LAYERS:
             raise FbpError(f"too many layers ({len(self.layer_sizes) - 1} > {_lib.FBP_MAX_LAYERS})")
         if jet.C > _lib.FBP_MAX_COMP:
@@ -46,14 +52,15 @@ class Plan:
         d.xd, d.ud, d.n_layers = jet.xd, jet.ud, len(self.layer_sizes) - 1
         for i, v in enumerate(self.layer_sizes):
             d.layer_sizes[i] = v
-        d.activation, d.window, d.n_comp = 0, 0, jet.C
+        d.activation, d.window, d.n_comp = self.ACTIVATIONS[activation], 0, jet.C
         for c in range(jet.C):
             d.comp_k[c], d.comp_l[c] = jet.comp_k[c], jet.comp_l[c]
         h = C.c_void_p()
         check(lib.fbp_plan_create(C.byref(h), C.byref(d)), "fbp_plan_create")
         self._h = h
         self.P = int(lib.fbp_plan_param_count(h))
-        self.set_kernel(kernel)
+        self.n_extra = int(lib.fbp_plan_n_extra(h))
+        self.set_kernel(kernel if activation == "tanh" else "auto")
 
     def set_kernel(self, kernel):
         lib = _lib.load()
@@ -85,16 +92,22 @@ class Plan:
 
 
 def pack_params(plan, layers):
-    """[(w (m,out,in), b (m,out)), ...] CUDA float32 -> packed (m, P)."""
+    """[(w (m,out,in), b (m,out), [activation parameters (m,out) ...]), ...] CUDA float32 -> packed (m, P)."""
     lib = _lib.load()
     m = layers[0][0].shape[0]
     packed = torch.empty((m, plan.P), dtype=torch.float32, device=layers[0][0].device)
-    ws = [w.contiguous().float() for w, _ in layers]
-    bs = [b.contiguous().float() for _, b in layers]
+    ws = [leaf[0].contiguous().float() for leaf in layers]
+    bs = [leaf[1].contiguous().float() for leaf in layers]
     n = len(layers)
     wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
     bp = (C.c_void_p * n)(*[b.data_ptr() for b in bs])
     check(lib.fbp_pack_params(plan.handle, m, wp, bp, ptr(packed), stream_ptr()), "fbp_pack_params")
+    for l, leaf in enumerate(layers):
+        if len(leaf) != 2 + plan.n_extra:
+            raise FbpError(f"layer {l} has {len(leaf)} leaves, the plan's activation expects {2 + plan.n_extra}")
+        for e in range(plan.n_extra):
+            v = leaf[2 + e].contiguous().float()
+            check(lib.fbp_pack_extra(plan.handle, m, l, e, ptr(v), ptr(packed), 1, stream_ptr()), "fbp_pack_extra")
     return packed
 
 
@@ -107,8 +120,15 @@ def unpack_params(plan, packed):
     n = len(ws)
     wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
     bp = (C.c_void_p * n)(*[b.data_ptr() for b in bs])
-    check(lib.fbp_unpack_params(plan.handle, m, ptr(packed.contiguous()), wp, bp, stream_ptr()), "fbp_unpack_params")
-    return list(zip(ws, bs))
+    packed = packed.contiguous()
+    check(lib.fbp_unpack_params(plan.handle, m, ptr(packed), wp, bp, stream_ptr()), "fbp_unpack_params")
+    extras = [[] for _ in ws]
+    for l, o in enumerate(ls[1:]):
+        for e in range(plan.n_extra):
+            v = torch.empty((m, o), dtype=torch.float32, device=packed.device)
+            check(lib.fbp_pack_extra(plan.handle, m, l, e, ptr(v), ptr(packed), 0, stream_ptr()), "fbp_pack_extra")
+            extras[l].append(v)
+    return [(w, b) + tuple(ex) for w, b, ex in zip(ws, bs, extras)]
 
 
 # --------------------------------------------------------------------------------------------------- decomposition on device

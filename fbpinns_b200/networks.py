@@ -207,6 +207,30 @@ class FourierFCN(FCN):
         return w @ x + b
 
 
+def kernel_layers(network, all_params, device=None):
+    """What the kernels need of a network: (activation tag of engine.Plan, layer sizes, [(W, b, activation parameters...)])
+    with every leaf carrying the leading subdomain axis.  For FourierFCN the static feature layer becomes layer 0,
+    W0 = [omega; omega], b0 = [0; pi/2], so that sin(W0 z + b0) = [sin(omega z), cos(omega z)] (fbpinns/networks.py:183-185)."""
+    act = getattr(network, "ACTIVATION", None)
+    if act is None:
+        raise NotImplementedError(f"{network} is not implemented by the B200 kernels")
+    to = (lambda t: t.to(device, torch.float32)) if device is not None else (lambda t: t.float())
+    layers = [tuple(to(t) for t in leaf) for leaf in all_params["trainable"]["network"]["subdomain"]["layers"]]
+    if act == "fourier_tanh":
+        omega = to(all_params["static"]["network"]["subdomain"]["omega"])           # (m, n_features, xd)
+        m, nf, _ = omega.shape
+        b0 = torch.cat([torch.zeros((m, nf), dtype=omega.dtype, device=omega.device),
+                        torch.full((m, nf), float(np.pi / 2), dtype=omega.dtype, device=omega.device)], dim=1)
+        layers = [(torch.cat([omega, omega], dim=1).contiguous(), b0)] + layers
+    sizes = [int(layers[0][0].shape[2])] + [int(leaf[0].shape[1]) for leaf in layers]
+    return act, sizes, layers
+
+
+def from_kernel_layers(network, layers):
+    "inverse of kernel_layers for the trainable leaves (drops FourierFCN's static feature layer)"
+    return layers[1:] if getattr(network, "ACTIVATION", None) == "fourier_tanh" else layers
+
+
 def norm(mu, sd, x):
     return (x - mu) / sd
 

@@ -270,7 +270,7 @@ def sharded_sum(sev, params, grads, tape_hook, weight):
 # --------------------------------------------------------------------------------------------------- update inputs / step
 
 def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, constraints_global, constraint_offsets,
-                              jets, layer_sizes, kernel="auto"):
+                              jets, layer_sizes, kernel="auto", activation="tanh"):
     """Sharded counterpart of trainers.get_update_inputs: the global active-set algebra is identical on every rank
     (every rank holds the full point set and the full static decomposition — both small), then takes are built for
     this rank's block of subdomains over the points inside them."""
@@ -322,7 +322,7 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
         halo = build_halo_lists(np.stack(inside), shard.rank)
         lips = torch.as_tensor(halo["local_ips"].astype(np.int32), dtype=torch.int32, device=dev)
         x_loc = gather_rows(x_ic, lips)
-        plan = Plan(layer_sizes, jets[ic], kernel=kernel)
+        plan = Plan(layer_sizes, jets[ic], kernel=kernel, activation=activation)
         takes = DeviceTakes(dd, x_loc, pos_loc, all_loc, len(a_loc), tile_points=plan.tile_points)
         ev = ConstraintEvaluator(plan, takes, x_loc, dd)
         sev = ShardedEvaluator(ev, halo, shard)

@@ -54,7 +54,7 @@ class UpdateInputs:
 
 
 def get_update_inputs(active, all_params, dd, x_batch_global, constraints_global, constraint_offsets,
-                      jets, layer_sizes, kernel="auto"):
+                      jets, layer_sizes, kernel="auto", activation="tanh"):
     """Device implementation of FBPINNTrainer._get_x_batch + _get_update_inputs (index side).
     constraints_global[ic] = list of per-point CUDA tensors of constraint ic (first is its x_batch)."""
     m = dd.m
@@ -91,7 +91,7 @@ def get_update_inputs(active, all_params, dd, x_batch_global, constraints_global
     out.x_batch, out.constraints, out.training_ips, out.constraint_ips, out.d = x_batch, constraints, training_ips, constraint_ips, d_stat
     out.takess, out.evaluators = [], []
     for ic, con in enumerate(constraints):
-        plan = Plan(layer_sizes, jets[ic], kernel=kernel)
+        plan = Plan(layer_sizes, jets[ic], kernel=kernel, activation=activation)
         takes = DeviceTakes(dd, con[0], pos, all_ims, len(active_ims), tile_points=plan.tile_points)
         out.takess.append(takes)
         out.evaluators.append(ConstraintEvaluator(plan, takes, con[0], dd))
@@ -238,8 +238,9 @@ class FBPINNTrainer(_Trainer):
         logger.info(f"Total number of subdomains: {m}")
 
         network = c.network
-        if network is not networks.FCN and not (isinstance(network, type) and issubclass(network, networks.FCN)):
-            raise NotImplementedError(f"{network} is not implemented by the B200 kernels (FCN with tanh only)")
+        if getattr(network, "ACTIVATION", None) is None or not hasattr(network, "init_params_batched"):
+            raise NotImplementedError(f"{network} is not implemented by the B200 kernels (FCN, AdaptiveFCN, SIREN, "
+                                      f"AdaptiveSIREN and FourierFCN are)")
         if not issubclass(decomposition, decompositions.RectangularDecompositionND):
             raise NotImplementedError(f"{decomposition} is not implemented by the B200 kernels "
                                       f"(RectangularDecompositionND family with the cosine window only)")
@@ -266,7 +267,8 @@ class FBPINNTrainer(_Trainer):
         domain, problem, decomposition = c.domain, c.problem, c.decomposition
         m = all_params["static"]["decomposition"]["m"]
         ud, xd = all_params["static"]["problem"]["dims"]
-        self.layer_sizes = list(c.network_init_kwargs["layer_sizes"])
+        # kernel view of the network: activation tag, layer sizes and leaves (FourierFCN gains its static feature layer)
+        self.activation, self.layer_sizes, layers = networks.kernel_layers(c.network, all_params, dev)
         self.dd = decomposition._device(all_params, dev)
 
         # constraints (fbpinns/trainers.py:436-461)
@@ -285,8 +287,8 @@ class FBPINNTrainer(_Trainer):
         logger.info(f"Total number of constraints: {len(self.constraints_global)}")
 
         # packed parameters + problem trainables + Adam
-        self.value_plan = Plan(self.layer_sizes, JetSpec(tuple((iu, ()) for iu in range(ud)), xd, ud), kernel=c.kernel)
-        layers = [(w.to(dev), b.to(dev)) for w, b in all_params["trainable"]["network"]["subdomain"]["layers"]]
+        self.value_plan = Plan(self.layer_sizes, JetSpec(tuple((iu, ()) for iu in range(ud)), xd, ud), kernel=c.kernel,
+                               activation=self.activation)
         self.params = pack_params(self.value_plan, layers)
         prob_tr = all_params["trainable"].get("problem", {})
         prob_keys = list(prob_tr.keys())
@@ -330,14 +332,15 @@ class FBPINNTrainer(_Trainer):
         shard = getattr(self, "shard", None)
         if shard is None or shard.world == 1:
             self.inputs = get_update_inputs(active, self.all_params, self.dd, self.x_batch_global, self.constraints_global,
-                                            self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel)
+                                            self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel,
+                                            activation=self.activation)
             self.update = UpdateStep(self.inputs, self.params, self.adam, self.all_params, self.prob_flat, c.problem,
                                      c.use_cuda_graph)
         else:
             from . import parallel
             self.inputs = parallel.get_update_inputs_sharded(shard, active, self.all_params, self.dd, self.x_batch_global,
                                                              self.constraints_global, self.constraint_offsets, self.jets,
-                                                             self.layer_sizes, kernel=c.kernel)
+                                                             self.layer_sizes, kernel=c.kernel, activation=self.activation)
             self.update = parallel.make_sharded_update(UpdateStep)(shard, self.inputs, self.params, self.adam,
                                                                    self.all_params, self.prob_flat, c.problem,
                                                                    c.use_cuda_graph)
@@ -394,8 +397,8 @@ class FBPINNTrainer(_Trainer):
         return self.export_all_params()
 
     def export_all_params(self):
-        "all_params with the reference's pytree leaves: layers = [(w (m,out,in), b (m,out)), ...]"
-        layers = unpack_params(self.value_plan, self.params)
+        "all_params with the reference's pytree leaves: layers = [(w (m,out,in), b (m,out), activation parameters...), ...]"
+        layers = networks.from_kernel_layers(self.c.network, unpack_params(self.value_plan, self.params))
         self.all_params["trainable"]["network"]["subdomain"]["layers"] = layers
         return self.all_params
 

@@ -54,7 +54,15 @@ extern "C" {
 #define FBP_BWD_NO_REDUCE 2
 #define FBP_BWD_REDUCE_ONLY 4
 
-#define FBP_ACT_TANH 0      /* FCN, fbpinns/networks.py:61-68 */
+#define FBP_ACT_TANH 0            /* FCN, fbpinns/networks.py:61-68 */
+/* The reference's other Network plug-ins (generic kernel family only).  Packed parameter row: per layer W, b, then
+ * the layer's per-unit activation parameters (every layer carries them, the last layer's are unused like in the
+ * reference's pytree): */
+#define FBP_ACT_ADAPTIVE_TANH 1   /* AdaptiveFCN  a * tanh(x / a),   extra: a          networks.py:70-101 */
+#define FBP_ACT_SIN 2             /* SIREN        sin(x)                               networks.py:103-133 */
+#define FBP_ACT_ADAPTIVE_SIN 3    /* AdaptiveSIREN c * sin(o * x),   extras: c, o      networks.py:135-166 */
+#define FBP_ACT_FOURIER_TANH 4    /* FourierFCN: layer 0 is the STATIC feature layer sin(W0 z + b0) with W0 = [omega; omega],
+                                   * b0 = [0; pi/2] (= [sin, cos] features, no gradient), then tanh layers  networks.py:168-194 */
 #define FBP_WINDOW_COSINE 0 /* windows.cosine, fbpinns/windows.py:25-35 */
 
 typedef struct fbp_plan fbp_plan;                    /* opaque */
@@ -136,6 +144,11 @@ int fbp_pack_params(const fbp_plan* plan, int64_t m, const float* const* d_w, co
                     float* d_params, void* stream);
 int fbp_unpack_params(const fbp_plan* plan, int64_t m, const float* d_params, float* const* d_w,
                       float* const* d_b, void* stream);
+/* Per-unit activation parameters of layer `layer` (which = 0: a / c, 1: o) as an [m][out] array <-> packed rows
+ * (to_packed != 0: array -> rows).  Only for plans whose activation has such parameters (FBP_ACT_ADAPTIVE_*). */
+int fbp_pack_extra(const fbp_plan* plan, int64_t m, int32_t layer, int32_t which, float* d_vec, float* d_params,
+                   int32_t to_packed, void* stream);
+int32_t fbp_plan_n_extra(const fbp_plan* plan);           /* activation parameters per unit: 0, 1 or 2 */
 
 /* ---- index construction (A2-A4): inside_points / inside_models / get_inputs on the device --- */
 /* Phase 1: per-point and per-model inside counts of x against the boxes of `d_models` (NULL = all m).

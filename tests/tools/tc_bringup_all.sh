@@ -10,6 +10,7 @@ mkdir -p gpurun_out
 OUT=gpurun_out
 timeout 120 python tests/tools/tc_capi_check.py all                 > $OUT/tcall_1_capi.log 2>&1
 FBP_TC_TESTS=1 timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu > $OUT/tcall_2_pytest.log 2>&1
+FBP_ACT_TESTS=1 timeout 300 python -m pytest tests/test_gpu_networks.py -q -m gpu > $OUT/tcall_2b_networks.log 2>&1
 timeout 300 python tests/tools/tc_bringup.py                         > $OUT/tcall_3_fwd.log 2>&1
 timeout 300 python tests/tools/tc_bringup_bwd.py                     > $OUT/tcall_4_bwd.log 2>&1
 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5                       > $OUT/tcall_5_bench_auto.json 2> $OUT/tcall_5_bench_auto.err
@@ -18,5 +19,5 @@ FBP_TC_FWD=2 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --ker
 if [ "$1" == "ncu" ]; then
   KERNEL=tensor-full timeout 600 bash profiles/run_ncu.sh r2tc
 fi
-tail -3 $OUT/tcall_1_capi.log $OUT/tcall_2_pytest.log $OUT/tcall_3_fwd.log $OUT/tcall_4_bwd.log
+tail -3 $OUT/tcall_1_capi.log $OUT/tcall_2_pytest.log $OUT/tcall_2b_networks.log $OUT/tcall_3_fwd.log $OUT/tcall_4_bwd.log
 tail -c 600 $OUT/tcall_5_bench_auto.json $OUT/tcall_5_bench_full.json $OUT/tcall_5_bench_full_v2.json
