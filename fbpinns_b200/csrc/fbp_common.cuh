@@ -1,7 +1,11 @@
 // Internal definitions shared by the kernels of libfbpinn_b200 (sm_100a only).
 #pragma once
 
+#ifdef FBP_HOST_EMU
+#include "fbp_host_emu.h"      // tests/tools: the per-pair kernels compiled as plain C++ for the CPU emulation test
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -97,16 +101,20 @@ struct fbp_plan {
 // ---------------------------------------------------------------------------------------------------
 // device math
 // ---------------------------------------------------------------------------------------------------
-#ifdef __CUDACC__
+#if defined(__CUDACC__) || defined(FBP_HOST_EMU)
 
 // tanh with ~1.5e-7 absolute error in 5 instructions: 1 - 2/(exp(2x)+1) with exp through MUFU.EX2
 // (ex2.approx.ftz) and the reciprocal through MUFU.RCP (rcp.approx.ftz), folded into one FFMA.
 // Saturates correctly: x -> +inf gives e = inf -> rcp = 0 -> 1 ; x -> -inf gives e = 0 -> 1 - 2 = -1.
 __device__ __forceinline__ float fbp_tanh(float x) {
+#ifdef FBP_HOST_EMU
+    return tanhf(x);
+#else
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
+#endif
 }
 
 // Per-dimension cosine window f(z) = ((1+cos(pi z))/2)^2 with z = (x-mu)/sd and its x-derivatives:

@@ -317,6 +317,7 @@ int64_t chunk_pairs(const PlanDev& pd, int64_t pairs, int64_t scratch_floats, in
 
 }  // namespace
 
+#ifndef FBP_HOST_EMU      // launch glue (the CPU emulation test calls the kernels above directly)
 int fbp_generic_act_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_params,
                             const float* d_sub_static, float* d_pair_out, float* d_scratch, int64_t scratch_floats,
                             cudaStream_t stream) {
@@ -380,3 +381,4 @@ extern "C" int fbp_pack_extra(const fbp_plan* plan, int64_t m, int32_t layer, in
     FBP_LAUNCH_CHECK();
     return 0;
 }
+#endif  // FBP_HOST_EMU

@@ -260,3 +260,108 @@ def test_activation_jet_formulas_match_autograd(kind):
     assert np.allclose(ab, ab_ref, rtol=1e-10, atol=1e-10)
     for got, ref in zip(pbar, pb_ref):
         assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["adaptive_fcn", "siren", "adaptive_siren", "fourier"])
+def test_activation_variant_kernels_emulated_on_cpu_match_oracle(name, tmp_path):
+    """csrc/fbp_generic_act.cu — the kernels' OWN SOURCE compiled as plain C++ (tests/tools/fbp_host_emu.h) and run one
+    pair at a time on the CPU — against the oracle: per-pair numerator jets (including a mixed second derivative) and
+    the gradients of every parameter leaf for a random cotangent.  This pins the kernels' indexing and arithmetic
+    before any GPU time is spent on them (float32 kernels vs float64 oracle: 2e-5 relative)."""
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    from fbpinns_b200 import _lib
+    from fbpinns_b200.engine import Plan
+    from fbpinns_b200 import networks as N
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libemu_act.so")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(root, "tests", "tools"),
+                        "-I" + os.path.join(root, "fbpinns_b200", "csrc"), "-o", so,
+                        os.path.join(root, "tests", "tools", "emu_generic_act.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    emu = C.CDLL(so)
+
+    cls, oname, n_extra = {"adaptive_fcn": (N.AdaptiveFCN, "adaptive_fcn", 1), "siren": (N.SIREN, "siren", 0),
+                           "adaptive_siren": (N.AdaptiveSIREN, "adaptive_siren", 2), "fourier": (N.FourierFCN, "fourier", 0)}[name]
+    rng = np.random.default_rng(5)
+    xd, m, nf = 2, 3, 2
+    counts = [7, 4, 6]
+    s = sum(counts)
+    hidden = [xd, 5, 4, 1]
+    sizes = ([2 * nf] + hidden[1:]) if name == "fourier" else hidden
+    layers = []
+    for fi, fo in zip(sizes[:-1], sizes[1:]):
+        v = np.sqrt((6.0 if "siren" in name else 1.0) / fi)
+        leaf = [rng.uniform(-v, v, (m, fo, fi)), rng.uniform(-v, v, (m, fo))] + [rng.uniform(0.6, 1.4, (m, fo)) for _ in range(n_extra)]
+        layers.append(tuple(t.astype(np.float32) for t in leaf))
+    ap = {"static": {}, "trainable": {"network": {"subdomain": {"layers": [tuple(torch.tensor(t) for t in leaf) for leaf in layers]}}}}
+    omega = None
+    if name == "fourier":
+        omega = (2 * np.pi * (0.1 + 0.3 * rng.standard_normal((m, nf, xd)))).astype(np.float32)
+        ap["static"]["network"] = {"subdomain": {"omega": torch.tensor(omega)}}
+    activation, ksizes, klayers = N.kernel_layers(cls, ap, "cpu")
+    req = ((0, ()), (0, (0,)), (0, (1,)), (0, (0, 0)), (0, (0, 1)), (0, (1, 1)))
+    jet = JetSpec(req, xd, 1)
+    plan = Plan(ksizes, jet, activation=activation)
+    P, Cj = plan.P, jet.C
+    # packed rows in the documented layout: per layer W, b, activation parameters
+    params = np.concatenate([np.concatenate([t.reshape(m, -1).numpy() for t in leaf], axis=1) for leaf in klayers], axis=1).astype(np.float32)
+    assert params.shape == (m, P)
+    lo = rng.uniform(-1, 0, (m, xd)).astype(np.float32)
+    hi = (lo + rng.uniform(0.5, 1.5, (m, xd))).astype(np.float32)
+    sub_static = np.ascontiguousarray(np.concatenate([lo, hi, np.ones((m, 1)), np.full((m, 1), 0.1), np.full((m, 1), 1.3)], axis=1), dtype=np.float32)
+    sub_of_pair = np.repeat(np.arange(m), counts).astype(np.int32)
+    x = (lo[sub_of_pair] + (hi - lo)[sub_of_pair] * rng.uniform(0.05, 0.95, (s, xd))).astype(np.float32)
+    ident = np.arange(s, dtype=np.int32)
+    sub_ids = np.arange(m, dtype=np.int32)
+    tv = _lib.TakesView()
+    tv.n, tv.s, tv.q, tv.s_active = s, s, s, s
+    tv.m_all, tv.m_active, tv.npou = m, m, 1
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    tv.d_sub_ids, tv.d_spair_point, tv.d_spair_row, tv.d_spair_sub = vp(sub_ids), vp(ident), vp(ident), vp(sub_of_pair)
+    scratch = np.zeros(max(plan.scratch_per_pair, 1) * s, dtype=np.float32)
+    pair_out = np.full((s, Cj), np.nan, dtype=np.float32)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.emu_act_forward(plan.handle, C.byref(tv), fp(x), fp(params), fp(sub_static), fp(pair_out), fp(scratch))
+    grow = rng.standard_normal((s, Cj)).astype(np.float32)
+    grads = np.zeros((m, P), dtype=np.float32)
+    emu.emu_act_backward(plan.handle, C.byref(tv), fp(x), fp(params), fp(sub_static), fp(grow), fp(grads), fp(scratch))
+
+    # ---- oracle, float64: every pair is a "point" of its own
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    lt = [tuple(T(t).requires_grad_(True) for t in leaf) for leaf in layers]
+    sp = torch.as_tensor(sub_of_pair, dtype=torch.long)
+    ps_take = [T(lo)[sp], T(hi)[sp], None, None, torch.ones((s, 1), dtype=torch.float64),
+               torch.tensor([[0.1, 1.3]], dtype=torch.float64).expand(s, 2)]
+    static_take = None if omega is None else {"omega": T(omega)[sp]}
+
+    def u_fn(xb):
+        return ref_model.model_inner(ps_take, [tuple(t[sp] for t in leaf) for leaf in lt], xb, oname, static_take)[0], ()
+    ujs = ref_model.get_ujs(T(x), ref_model.get_jmaps(req), u_fn)
+    L = 0.0
+    for (iu, p), ref in zip(req, ujs):
+        col = jet.column(iu, p)
+        e = np.abs(pair_out[:, col] - ref[:, 0].detach().numpy()).max() / max(ref.detach().abs().max().item(), 1e-30)
+        assert e < 2e-5, f"{name} d{p}: {e:.2e}"
+        L = L + (T(grow[:, col]) * ref[:, 0]).sum()
+    ref_grads = torch.autograd.grad(L, [t for leaf in lt for t in leaf], allow_unused=True)
+    # split the emulated gradient rows by the packed layout
+    off, got = 0, []
+    for leaf in klayers:
+        for t in leaf:
+            nel = int(np.prod(t.shape[1:]))
+            got.append(grads[:, off:off + nel].reshape((m,) + tuple(t.shape[1:])))
+            off += nel
+    if name == "fourier":
+        assert np.all(got[0] == 0) and np.all(got[1] == 0)          # static feature layer: no gradient
+        got = got[2:]
+    for g, rg in zip(got, ref_grads):
+        if rg is None:
+            assert np.all(g == 0)
+            continue
+        e = np.abs(g - rg.numpy()).max() / max(np.abs(rg.numpy()).max(), 1e-30)
+        assert e < 2e-5, f"{name} gradient leaf {tuple(g.shape)}: {e:.2e}"
