@@ -14,6 +14,7 @@ What differs from the reference by design:
 Out of scope: PINNTrainer, plotting, tensorboard, model checkpoint files.
 """
 
+import os
 import time
 
 import numpy as np
@@ -390,11 +391,64 @@ class FBPINNTrainer(_Trainer):
             lossval = self.step()
             u_test_losses, start1, report_time = self._report(
                 i + 1, u_test_losses, start0, start1, report_time, self.u_exact, self.x_batch_test, lossval)
+            if getattr(c, "save_models", False) and (i + 1) % c.model_save_freq == 0:        # off by default
+                self.save_model(i + 1, self.inputs.active, u_test_losses)
 
         torch.cuda.synchronize()
         logger.info(f"[i: {c.n_steps}/{c.n_steps}] Training complete")
         self.u_test_losses = u_test_losses
         return self.export_all_params()
+
+    # ---- checkpoints in the reference's format (fbpinns/trainers_base.py:64-69, trainers.py:721) ---------------------
+    def _adam_trees(self):
+        "mu / nu as trees with the structure of all_params['trainable']"
+        trees = []
+        for buf, pbuf in ((self.adam.mu, self.adam.pmu), (self.adam.nu, self.adam.pnu)):
+            t = {"network": {"subdomain": {"layers": networks.from_kernel_layers(self.c.network, unpack_params(self.value_plan, buf))}}}
+            prob = self.all_params["trainable"].get("problem", {})
+            if prob:
+                t["problem"], off = {}, 0
+                for k, v in prob.items():
+                    t["problem"][k] = pbuf[off:off + v.numel()].view(v.shape)
+                    off += v.numel()
+            trees.append(t)
+        return trees
+
+    def save_model(self, i, active, u_test_losses=(), path=None):
+        "model_{i:08d}.jax = pickle of (i, all_params, optax-adam state, active, u_test_losses), numpy leaves"
+        from .util import checkpoint
+        mu, nu = self._adam_trees()
+        path = path or os.path.join(getattr(self.c, "model_out_dir", "."), f"model_{i:08d}.jax")
+        checkpoint.save_model(path, i, self.export_all_params(), mu, nu, int(self.adam.count.item()), active, u_test_losses)
+        return path
+
+    def load_model(self, path):
+        """Resume from a checkpoint written by save_model or by the reference (same network and decomposition): parameters,
+        problem trainables and the Adam state go back into the packed device buffers.  Returns (i, active, u_test_losses);
+        call set_active(active) afterwards."""
+        from .util import checkpoint
+        i, ap, (count, mu, nu), active, losses = checkpoint.load_model(path)
+        dev = self.params.device
+        tens = lambda tree: [tuple(torch.as_tensor(np.asarray(t), dtype=torch.float32, device=dev) for t in leaf)
+                             for leaf in tree["network"]["subdomain"]["layers"]]
+
+        def kernel_rows(tree):
+            probe = {"static": self.all_params["static"], "trainable": {"network": {"subdomain": {"layers": tens(tree)}}}}
+            return pack_params(self.value_plan, networks.kernel_layers(self.c.network, probe, dev)[2])
+        self.params.copy_(kernel_rows(ap["trainable"]))
+        self.adam.mu.copy_(kernel_rows(mu))
+        self.adam.nu.copy_(kernel_rows(nu))
+        if self.c.network.ACTIVATION == "fourier_tanh":      # the static feature rows carry no optimiser state
+            n0 = self.layer_sizes[0] * self.layer_sizes[1] + self.layer_sizes[1]
+            self.adam.mu[:, :n0] = 0
+            self.adam.nu[:, :n0] = 0
+        self.adam.count.fill_(int(count))
+        if self.prob_flat is not None:
+            for dst, tree in ((self.prob_flat, ap["trainable"]), (self.adam.pmu, mu), (self.adam.pnu, nu)):
+                flat = torch.cat([torch.as_tensor(np.asarray(tree["problem"][k]), dtype=torch.float32).reshape(-1)
+                                  for k in self.all_params["trainable"]["problem"]])
+                dst[:flat.numel()].copy_(flat.to(dev))
+        return i, active, losses
 
     def export_all_params(self):
         "all_params with the reference's pytree leaves: layers = [(w (m,out,in), b (m,out), activation parameters...), ...]"

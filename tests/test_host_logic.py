@@ -305,3 +305,33 @@ def test_jax_prng_known_answers():
         for (W, B), (w, b) in zip(batched["layers"], single["layers"]):
             assert torch.equal(W[i], w) and torch.equal(B[i], b)
             assert float(w.abs().max()) <= 1 / np.sqrt(w.shape[1]) and w.dtype == torch.float32
+
+
+def test_checkpoint_is_in_the_reference_pickle_format(tmp_path):
+    """util/checkpoint.py: model_{i:08d}.jax = pickle of (i, all_params, (ScaleByAdamState(count, mu, nu), EmptyState()),
+    active, u_test_losses) with numpy leaves (fbpinns/trainers_base.py:64-69, trainers.py:721); the optax classes are
+    referenced by their real module paths, so the file loads where optax exists and round-trips here without it."""
+    import pickle
+    import pickletools
+    from fbpinns_b200.util import checkpoint as ck
+    rng = np.random.default_rng(0)
+    layers = [(torch.tensor(rng.standard_normal((3, 4, 2)), dtype=torch.float32), torch.tensor(rng.standard_normal((3, 4)), dtype=torch.float32))]
+    all_params = {"static": {"problem": {"dims": (1, 2)}, "decomposition": {"m": 3, "_device_cache": object()}},
+                  "trainable": {"network": {"subdomain": {"layers": layers}}, "problem": {"mu": torch.tensor(0.5)}}}
+    mu = {"network": {"subdomain": {"layers": [(torch.zeros(3, 4, 2), torch.ones(3, 4))]}}, "problem": {"mu": torch.tensor(0.1)}}
+    path = str(tmp_path / "model_00000010.jax")
+    ck.save_model(path, 10, all_params, mu, mu, 10, np.array([1, 2, 0]), [[0, 0.1, 0.5, 0.6]])
+    raw = open(path, "rb").read()
+    names = {arg for op, arg, _ in pickletools.genops(raw) if isinstance(arg, str)}
+    assert any("optax._src.transform" in n for n in names) and any("ScaleByAdamState" in n for n in names)
+    assert "optax" not in __import__("sys").modules or __import__("sys").modules["optax"].__name__ == "optax"
+    i, ap, (count, mu2, nu2), active, losses = ck.load_model(path)
+    assert i == 10 and count == 10 and active.tolist() == [1, 2, 0] and losses.shape == (1, 4)
+    assert "_device_cache" not in ap["static"]["decomposition"] and ap["static"]["problem"]["dims"] == (1, 2)
+    w, b = ap["trainable"]["network"]["subdomain"]["layers"][0]
+    assert isinstance(w, np.ndarray) and np.array_equal(w, layers[0][0].numpy()) and isinstance(ap["trainable"]["network"]["subdomain"]["layers"][0], tuple)
+    assert np.array_equal(mu2["network"]["subdomain"]["layers"][0][1], np.ones((3, 4), dtype=np.float32))
+    # the raw pickle has the reference's outer structure
+    with ck.optax_classes():
+        model = pickle.loads(raw)
+    assert isinstance(model, tuple) and len(model) == 5 and type(model[2][0]).__name__ == "ScaleByAdamState" and model[2][1] == ()
