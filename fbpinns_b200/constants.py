@@ -99,7 +99,6 @@ class Constants(ConstantsBase):
         self.use_cuda_graph = True       # capture the whole step between active-set changes
         self.kernel = "auto"             # "auto" | "generic" | "tiled" | "tensor" | "tensor-full" (tcgen05 where an instance exists)
         self.save_models = False         # write model_{i:08d}.jax checkpoints (reference format) every model_save_freq steps
-        self.model_out_dir = "."
         self.init_prng = "numpy"         # "numpy" (default_rng(seed)) | "jax" (the reference's threefry key sequence, util/jax_prng.py)
 
         self.hostname = socket.gethostname().lower()

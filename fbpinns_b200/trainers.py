@@ -418,7 +418,8 @@ class FBPINNTrainer(_Trainer):
         "model_{i:08d}.jax = pickle of (i, all_params, optax-adam state, active, u_test_losses), numpy leaves"
         from .util import checkpoint
         mu, nu = self._adam_trees()
-        path = path or os.path.join(getattr(self.c, "model_out_dir", "."), f"model_{i:08d}.jax")
+        path = path or os.path.join(self.c.model_out_dir, f"model_{i:08d}.jax")
+        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
         checkpoint.save_model(path, i, self.export_all_params(), mu, nu, int(self.adam.count.item()), active, u_test_losses)
         return path
 
