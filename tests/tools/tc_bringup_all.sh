@@ -16,6 +16,7 @@ timeout 300 python tests/tools/tc_bringup_bwd.py                     > $OUT/tcal
 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5                       > $OUT/tcall_5_bench_auto.json 2> $OUT/tcall_5_bench_auto.err
 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --kernel tensor-full  > $OUT/tcall_5_bench_full.json 2> $OUT/tcall_5_bench_full.err
 FBP_TC_FWD=2 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --kernel tensor-full > $OUT/tcall_5_bench_full_v2.json 2> $OUT/tcall_5_bench_full_v2.err
+timeout 300 python tests/tools/bench_schedule.py --steps 2000 > $OUT/tcall_7_schedule_cfg3.json 2> $OUT/tcall_7_schedule_cfg3.err
 if [ "$1" == "ncu" ]; then
   KERNEL=tensor-full timeout 600 bash profiles/run_ncu.sh r2tc
 fi
