@@ -106,6 +106,72 @@ extern "C" int fbp_tc_selftest(const float* d_a, const float* d_w, float* d_out,
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// Self-test of the MN-major shared-memory operand form the planned tensor-core weight gradient needs:
+// out[128][64] = sum_p A[p][m] * B[p][n] over 128 "points" p, A (128 x 128) and B (128 x 64) staged row-by-row (one
+// thread = one p, as the point warps would) in the canonical MN-major no-swizzle layout, both operands from shared
+// memory (".ss" form), 16 MMAs with M = 128, N = 64, K = 8.  Inputs are rounded to TF32 so that one pass is exact up to
+// FP32 accumulation.  variant bit 0: swap LBO and SBO.
+// -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tc_selftest_mn_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                                float* __restrict__ out, int variant) {
+    extern __shared__ __align__(128) float smn[];
+    float* as = smn;                      // 128 x 128
+    float* bs = smn + 128 * 128;          // 128 x 64
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = warp_uniform();
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int m = 0; m < 128; ++m) as[mncore_index(m, tid, 128)] = __uint_as_float(tf32_rn(A[tid * 128 + m]));
+    for (int n = 0; n < 64; ++n) bs[mncore_index(n, tid, 64)] = __uint_as_float(tf32_rn(B[tid * 64 + n]));
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    if (warp == 0 && elect_one()) {
+        const uint32_t a_lbo = (variant & 1) ? MN_SBO : mn_lbo(128), a_sbo = (variant & 1) ? mn_lbo(128) : MN_SBO;
+        const uint32_t b_lbo = (variant & 1) ? MN_SBO : mn_lbo(64), b_sbo = (variant & 1) ? mn_lbo(64) : MN_SBO;
+        const uint64_t ad = make_smem_desc(smem_u32(as), a_lbo, a_sbo), bd = make_smem_desc(smem_u32(bs), b_lbo, b_sbo);
+        constexpr uint32_t idesc = make_idesc_tf32(128, 64, 1, 1);
+        for (int ks = 0; ks < 16; ++ks)     // one K group of 8 points per MMA: the next group starts LBO bytes further
+            mma_tf32_ss(tbase, ad + (uint64_t)((ks * mn_lbo(128)) >> 4), bd + (uint64_t)((ks * mn_lbo(64)) >> 4), idesc, ks != 0);
+        mma_commit(&bar);
+    }
+    mbar_wait_or_trap(&bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        uint32_t v[8];
+        tmem_ld8(tbase + lane_base + 8 * ch, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[tid * 64 + 8 * ch + e] = __uint_as_float(v[e]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 64);
+}
+
+extern "C" int fbp_tc_selftest_mn(const float* d_a, const float* d_b, float* d_out, int32_t variant, void* stream) {
+    FBP_REQUIRE(d_a && d_b && d_out, "fbp_tc_selftest_mn: null buffer");
+    constexpr int bytes = (128 * 128 + 128 * 64) * 4;
+    static bool configured = false;
+    if (!configured) {
+        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        configured = true;
+    }
+    tc_selftest_mn_kernel<<<1, 128, bytes, (cudaStream_t)stream>>>(d_a, d_b, d_out, variant);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // plan matching and launchers
 // -----------------------------------------------------------------------------------------------------------------
 int fbp_tc_supported(const FastSpec& f, int C) {

@@ -49,15 +49,23 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
     // base offset [49,52) = 0, lbo mode [52] = 0, layout type [61,64) = 0 (SWIZZLE_NONE)
     return d;
 }
-// instruction descriptor of tcgen05.mma.kind::tf32, FP32 accumulate, A and B K-major
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+// instruction descriptor of tcgen05.mma.kind::tf32, FP32 accumulate; a_mn / b_mn = 1: the operand is MN-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4)                    // [4,6)   D format F32
          | (2u << 7)                    // [7,10)  A format TF32
          | (2u << 10)                   // [10,13) B format TF32
-         | (0u << 15) | (0u << 16)      // A, B K-major
+         | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16)      // [15] A major, [16] B major (0 = K-major)
          | ((uint32_t)(N >> 3) << 17)   // [17,23) N >> 3
          | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
 }
+
+// canonical MN-major no-swizzle placement of element (mn, k) of an operand with MN rows of the MMA and K = contraction
+// index (floats): core matrices of 8 (K) x 4 (MN) elements stored as 128 contiguous bytes, the MN / 4 cores of one
+// K group contiguous (SBO = 128 B), K groups (8 per MMA) MN * 32 bytes apart (LBO).  Checked against CuTe's
+// Layout_MN_INTER_Atom in tests/tools/umma_desc_check.cu.
+__host__ __device__ constexpr int mncore_index(int mn, int k, int MN) { return (mn & 3) + (k & 7) * 4 + (mn >> 2) * 32 + (k >> 3) * (MN * 8); }
+constexpr uint32_t MN_SBO = 128;
+__host__ __device__ constexpr uint32_t mn_lbo(int MN) { return (uint32_t)MN * 32u; }
 
 // canonical K-major no-swizzle placement of element (row n, column k) of a [rows][32] tf32 matrix, in floats:
 // 8 x 4 core matrices of 32 floats, the 8 cores of a row group contiguous along K (LBO = 128 B), row groups 1024 B apart
@@ -102,6 +110,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr)
                  : "memory");
+}
+// D[tmem] (+)= A[smem descriptor] * B[smem descriptor]
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem descriptor]; one thread issues for the CTA
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {

@@ -8,6 +8,7 @@
 set -x
 mkdir -p gpurun_out
 OUT=gpurun_out
+timeout 120 python tests/tools/tc_selftest.py --mn                   > $OUT/tcall_0_selftest_mn.log 2>&1
 timeout 120 python tests/tools/tc_capi_check.py all                 > $OUT/tcall_1_capi.log 2>&1
 FBP_TC_TESTS=1 timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu > $OUT/tcall_2_pytest.log 2>&1
 FBP_ACT_TESTS=1 timeout 300 python -m pytest tests/test_gpu_networks.py -q -m gpu > $OUT/tcall_2b_networks.log 2>&1
@@ -20,5 +21,5 @@ timeout 300 python tests/tools/bench_schedule.py --steps 2000 > $OUT/tcall_7_sch
 if [ "$1" == "ncu" ]; then
   KERNEL=tensor-full timeout 600 bash profiles/run_ncu.sh r2tc
 fi
-tail -3 $OUT/tcall_1_capi.log $OUT/tcall_2_pytest.log $OUT/tcall_2b_networks.log $OUT/tcall_3_fwd.log $OUT/tcall_4_bwd.log
+tail -3 $OUT/tcall_0_selftest_mn.log $OUT/tcall_1_capi.log $OUT/tcall_2_pytest.log $OUT/tcall_2b_networks.log $OUT/tcall_3_fwd.log $OUT/tcall_4_bwd.log
 tail -c 600 $OUT/tcall_5_bench_auto.json $OUT/tcall_5_bench_full.json $OUT/tcall_5_bench_full_v2.json

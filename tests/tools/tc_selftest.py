@@ -16,7 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def run_variant(variant):
+def run_variant(variant, mn=False):
     rt = None
     for name in ("libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
         try:
@@ -27,8 +27,9 @@ def run_variant(variant):
     if rt is None:
         raise SystemExit("libcudart not found")
     lib = C.CDLL(os.path.join(ROOT, "fbpinns_b200", "csrc", "libfbpinn_b200.so"))
-    lib.fbp_tc_selftest.restype = C.c_int
-    lib.fbp_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    fn = lib.fbp_tc_selftest_mn if mn else lib.fbp_tc_selftest
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.fbp_last_error.restype = C.c_char_p
     rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
     rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
@@ -39,22 +40,32 @@ def run_variant(variant):
             raise SystemExit(f"{what}: cuda error {rc} {rt.cudaGetErrorString(rc).decode()}")
 
     rng = np.random.default_rng(0)
-    a = rng.standard_normal((128, 32)).astype(np.float32)
-    w = rng.uniform(-1, 1, (32, 32)).astype(np.float32)
-    out = np.full((128, 32), np.nan, dtype=np.float32)
+    if mn:      # out[m][n] = sum_p a[p][m] w[p][n], inputs pre-rounded to TF32 so that a single pass is exact
+        tf32 = lambda v: ((v.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
+        a = tf32(rng.standard_normal((128, 128)).astype(np.float32))
+        w = tf32(rng.uniform(-1, 1, (128, 64)).astype(np.float32))
+        out = np.full((128, 64), np.nan, dtype=np.float32)
+    else:
+        a = rng.standard_normal((128, 32)).astype(np.float32)
+        w = rng.uniform(-1, 1, (32, 32)).astype(np.float32)
+        out = np.full((128, 32), np.nan, dtype=np.float32)
     da, dw, do = C.c_void_p(), C.c_void_p(), C.c_void_p()
     for p, arr in ((da, a), (dw, w), (do, out)):
         ck(rt.cudaMalloc(C.byref(p), arr.nbytes), "cudaMalloc")
         ck(rt.cudaMemcpy(p, arr.ctypes.data_as(C.c_void_p), arr.nbytes, 1), "cudaMemcpy h2d")
-    rc = lib.fbp_tc_selftest(da, dw, do, variant, None)
+    rc = fn(da, dw, do, variant, None)
     if rc != 0:
         raise SystemExit("fbp_tc_selftest: " + (lib.fbp_last_error() or b"?").decode())
     ck(rt.cudaDeviceSynchronize(), "cudaDeviceSynchronize")
     ck(rt.cudaMemcpy(out.ctypes.data_as(C.c_void_p), do, out.nbytes, 2), "cudaMemcpy d2h")
-    ref = a.astype(np.float64) @ w.astype(np.float64).T
-    scale = (np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T).max()
+    if mn:
+        ref = a.astype(np.float64).T @ w.astype(np.float64)
+        scale = (np.abs(a).astype(np.float64).T @ np.abs(w).astype(np.float64)).max()
+    else:
+        ref = a.astype(np.float64) @ w.astype(np.float64).T
+        scale = (np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T).max()
     err = np.abs(out - ref)
-    res = {"variant": variant, "max_err_rel": float(np.nanmax(err) / scale), "nan": int(np.isnan(out).sum()),
+    res = {"form": "mn-major ss" if mn else "k-major ts", "variant": variant, "max_err_rel": float(np.nanmax(err) / scale), "nan": int(np.isnan(out).sum()),
            "bad_rows": int((err.max(axis=1) / scale > 1e-5).sum()), "bad_cols": int((err.max(axis=0) / scale > 1e-5).sum()),
            "out00": float(out[0, 0]), "ref00": float(ref[0, 0])}
     print(json.dumps(res))
@@ -62,13 +73,15 @@ def run_variant(variant):
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
-        run_variant(int(sys.argv[2]))
+        run_variant(int(sys.argv[2]), mn="--mn" in sys.argv)
         sys.exit(0)
-    variants = [int(v) for v in sys.argv[1:]] or [0, 4, 1, 2]
+    mn = "--mn" in sys.argv
+    variants = [int(v) for v in sys.argv[1:] if v != "--mn"] or ([0, 1] if mn else [0, 4, 1, 2])
     lines = []
     for v in variants:
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(v)], capture_output=True, text=True, timeout=60)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(v)] + (["--mn"] if mn else []),
+                               capture_output=True, text=True, timeout=60)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps(
                 {"variant": v, "failed": (r.stderr.strip().splitlines() or ["no output"])[-1], "rc": r.returncode})
         except subprocess.TimeoutExpired:
