@@ -183,11 +183,44 @@ def gather_rows(src, idx):
 
 # --------------------------------------------------------------------------------------------------- takes
 
-def build_work_items(sub_off, m_active, tile_points, target_items):
+def _split_tiles(ntiles, parts, split):
+    """Tile counts of the `parts` items a subdomain of `ntiles` tiles is cut into.  "equal": equal parts (round 1 default).
+    "guided": sizes fall off geometrically (weights 2^(n-1), ..., 2, 2 over n = parts + 1 items), so that with the
+    longest-first launch order the big items fill the whole waves and the small ones the last, partial wave — the
+    partial-wave tail of equal items is one candidate for what the reverse kernel loses at small per-GPU sizes.
+    Experimental knob (FBP_ITEM_SPLIT=guided): a list-scheduling model of the N = 8 case predicts NO gain over the equal
+    split with LPT order (packing efficiency 0.98 already), so it stays off until measured."""
+    if split == "guided" and parts >= 2 and ntiles >= parts + 1:
+        n = parts + 1
+        w = np.array([2.0 ** (n - 1 - i) for i in range(n - 1)] + [2.0])
+        sizes = np.maximum(1, np.floor(ntiles * w / w.sum()).astype(np.int64))
+        i = 0
+        while sizes.sum() < ntiles:              # hand the remainder out, largest first
+            sizes[i % n] += 1
+            i += 1
+        i = 0
+        while sizes.sum() > ntiles:              # only when the floor of 1 over-allocated
+            if sizes[i % n] > 1:
+                sizes[i % n] -= 1
+            i += 1
+        return [int(v) for v in sorted(sizes, reverse=True)]
+    size = -(-ntiles // parts)
+    out = []
+    left = ntiles
+    while left > 0:
+        out.append(min(size, left))
+        left -= out[-1]
+    return out
+
+
+def build_work_items(sub_off, m_active, tile_points, target_items, split=None):
     """Work list for the tiled kernels: (subdomain position, first pair, pair count, split index) rows, subdomain
-    major.  A subdomain is cut into equal chunks (whole numbers of tiles) so that the list has about `target_items`
-    entries when the problem is small and one entry per subdomain when it is large.  Also returns the launch orders
-    (longest item first, LPT) for the forward (all items) and reverse (active items) kernels."""
+    major.  A subdomain is cut into chunks of whole tiles so that the list has about `target_items` entries when the
+    problem is small and one entry per subdomain when it is large; `split` ("equal" | "guided", default from
+    FBP_ITEM_SPLIT, else "equal") chooses the chunk sizes (_split_tiles).  Also returns the launch orders (longest item
+    first, LPT) for the forward (all items) and reverse (active items) kernels."""
+    if split is None:
+        split = os.environ.get("FBP_ITEM_SPLIT", "equal")
     sub_off = np.asarray(sub_off, dtype=np.int64)
     m_all = len(sub_off) - 1
     s = int(sub_off[-1])
@@ -199,13 +232,11 @@ def build_work_items(sub_off, m_active, tile_points, target_items):
         cnt = b - a
         if cnt > 0:
             parts = -(-cnt // chunk0)
-            size = -(-(-(-cnt // parts)) // tile_points) * tile_points      # equal parts, rounded up to whole tiles
-            k = 0
-            while a < b:
-                c = min(size, b - a)
+            ntiles = -(-cnt // tile_points)
+            for k, nt in enumerate(_split_tiles(ntiles, min(parts, ntiles), split)):
+                c = min(nt * tile_points, b - a)
                 items.append((sp, a, c, k))
                 a += c
-                k += 1
         sub_item_off.append(len(items))
     items = np.asarray(items, dtype=np.int32).reshape(-1, 4)
     sub_item_off = np.asarray(sub_item_off, dtype=np.int32)

@@ -158,8 +158,9 @@ def test_work_items_cover_all_pairs():
     rng = np.random.default_rng(0)
     counts = rng.integers(0, 3000, size=50)
     sub_off = np.concatenate([[0], np.cumsum(counts)])
-    for tile, target in [(128, 1184), (64, 10), (128, 1)]:
-        items, sio, nia, of, ob = build_work_items(sub_off, 30, tile, target)
+    for tile, target, split in [(128, 1184, "equal"), (64, 10, "equal"), (128, 1, "equal"), (128, 1184, "guided"),
+                                (64, 400, "guided"), (128, 1, "guided")]:
+        items, sio, nia, of, ob = build_work_items(sub_off, 30, tile, target, split)
         assert np.array_equal(np.sort(of), np.arange(len(items))) and np.array_equal(np.sort(ob), np.arange(nia))
         assert (np.diff(items[of, 2]) <= 0).all() and (np.diff(items[ob, 2]) <= 0).all()
         assert items[:, 2].sum() == sub_off[-1]
