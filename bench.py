@@ -174,6 +174,10 @@ def run_ours(args):
     kw = dict(n_sub=FULL["n_sub"], n_pts=FULL["n_pts"], layer_sizes=layer_sizes)
     if args.small:
         kw.update(n_sub=(16, 16), n_pts=(256, 256))
+    if args.shape:          # debug / profiling shapes, e.g. one rank's share of an 8-GPU run on a single GPU: 8,64,128,1024
+        a_, b_, c_, d_ = (int(v) for v in args.shape.split(","))
+        kw.update(n_sub=(a_, b_), n_pts=(c_, d_))
+        args.small = True   # everything that labels / extrapolates the full workload treats it like --small
     if args.config == "cfg5":
         c = configs.cfg5_poisson(device=str(dev), use_cuda_graph=not args.no_graph, kernel=args.kernel, **kw)
     else:       # the other BASELINE configs at full size, all subdomains active (informational lines, not the headline)
@@ -334,7 +338,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": (WORKLOAD if args.config == "cfg5" else f"{args.config} (BASELINE config, all subdomains active)")
-                       if not args.small else "SMALL cfg5 16x16 subdomains 256x256 grid (debug)",
+                       if not args.small else f"DEBUG cfg5 {kw['n_sub'][0]}x{kw['n_sub'][1]} subdomains "
+                                                  f"{kw['n_pts'][0]}x{kw['n_pts'][1]} grid (not the headline workload)",
                        "layers": list(layer_sizes), "subdomains": m, "points": n_points_global,
                        "pairs_this_rank": s_local, "parallelism": f"subdomain-slabs x{world}" if world > 1 else "single GPU",
                        "cuda_graph": tr.update.graph is not None, "kernel_family": ("tensor forward + tensor reverse (tcgen05 3xTF32, weight gradient on FFMA2)" if ev.plan.kernel == "tensor-full" else
@@ -390,6 +395,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-rebuild", action="store_true")
+    ap.add_argument("--shape", default=None, help="cfg5 debug shape 'nsub0,nsub1,npts0,npts1' (labels the line as not the headline)")
     ap.add_argument("--small", action="store_true", help="debug-sized problem (not a valid bench number)")
     ap.add_argument("--config", default="cfg5", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
                     help="BASELINE config; cfg5 is the headline workload, the others are informational")
