@@ -92,10 +92,11 @@ struct fbp_plan {
     FastSpec fast;
     bool tc_ok;           // the tcgen05 ("tensor") family has an instance for this plan
     bool tc_auto;         // ... and that instance has been validated on hardware, so mode 0 picks it (FBP_TC_AUTO=0: never)
+    bool tc_auto_bwd;     // FBP_TC_AUTO=full: mode 0 also picks the tensor reverse kernel (switch for the next hardware session)
     int mode;             // 0 auto, 1 generic, 2 tiled, 3 tensor forward + tiled reverse, 4 tensor forward and reverse
     bool use_fast() const { return mode == 1 ? false : fast_id >= 0; }
     bool use_tc() const { return ((mode == 3 || mode == 4) && tc_ok) || (mode == 0 && tc_auto); }
-    bool use_tc_bwd() const { return mode == 4 && tc_ok; }
+    bool use_tc_bwd() const { return (mode == 4 && tc_ok) || (mode == 0 && tc_auto && tc_auto_bwd); }
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -123,7 +123,7 @@ int64_t fbp_plan_param_count(const fbp_plan* plan);       /* P */
 int32_t fbp_plan_is_fast(const fbp_plan* plan);           /* 1 if a tiled kernel instance covers this plan */
 int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile (work-list granularity) */
 /* Select kernel family: 0 = auto (tiled when available; the tensor forward where its instance has been validated on
- * hardware, unless the environment says FBP_TC_AUTO=0), 1 = force generic, 2 = force tiled (error if none),
+ * hardware, unless the environment says FBP_TC_AUTO=0; FBP_TC_AUTO=full adds the tensor reverse kernel), 1 = force generic, 2 = force tiled (error if none),
  * 3 = tensor: the forward hidden-layer GEMMs run on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy);
  *     needs H = 32, two hidden layers and at most 5 jet components (error otherwise).  The reverse kernel stays tiled.
  * 4 = tensor forward and the warp-specialised tensor reverse kernel (no activation cache; bring-up state). */

@@ -17,9 +17,11 @@ timeout 300 python tests/tools/tc_bringup_bwd.py                     > $OUT/tcal
 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5                       > $OUT/tcall_5_bench_auto.json 2> $OUT/tcall_5_bench_auto.err
 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --kernel tensor-full  > $OUT/tcall_5_bench_full.json 2> $OUT/tcall_5_bench_full.err
 FBP_TC_FWD=2 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --kernel tensor-full > $OUT/tcall_5_bench_full_v2.json 2> $OUT/tcall_5_bench_full_v2.err
+# the whole GPU suite with the tensor reverse kernel selected by auto mode (what flipping the default would run)
+FBP_TC_AUTO=full timeout 900 python -m pytest tests -x -q -m gpu > $OUT/tcall_6_pytest_auto_full.log 2>&1
 timeout 300 python tests/tools/bench_schedule.py --steps 2000 > $OUT/tcall_7_schedule_cfg3.json 2> $OUT/tcall_7_schedule_cfg3.err
 if [ "$1" == "ncu" ]; then
   KERNEL=tensor-full timeout 600 bash profiles/run_ncu.sh r2tc
 fi
-tail -3 $OUT/tcall_0_selftest_mn.log $OUT/tcall_1_capi.log $OUT/tcall_2_pytest.log $OUT/tcall_2b_networks.log $OUT/tcall_3_fwd.log $OUT/tcall_4_bwd.log
+tail -3 $OUT/tcall_6_pytest_auto_full.log $OUT/tcall_0_selftest_mn.log $OUT/tcall_1_capi.log $OUT/tcall_2_pytest.log $OUT/tcall_2b_networks.log $OUT/tcall_3_fwd.log $OUT/tcall_4_bwd.log
 tail -c 600 $OUT/tcall_5_bench_auto.json $OUT/tcall_5_bench_full.json $OUT/tcall_5_bench_full_v2.json
