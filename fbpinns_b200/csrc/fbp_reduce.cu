@@ -213,6 +213,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
     dst[e] = src[(int64_t)idx[i] * rf + k];
 }
 
+#ifndef FBP_HOST_EMU      // micro-benchmarks (inline PTX) and launch glue are not part of the CPU emulation build
 // ---- FP32 FMA peak micro-benchmark ------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
     float v[16];
@@ -252,9 +253,11 @@ __global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, 
 }
 
 inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
+#endif  // FBP_HOST_EMU
 
 }  // namespace
 
+#ifndef FBP_HOST_EMU
 extern "C" {
 
 int fbp_window_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x, const float* d_sub_static,
@@ -398,3 +401,4 @@ int fbp_fma_peak(int32_t iters, float* tflops, void* stream) { return fma_peak_i
 int fbp_ffma2_peak(int32_t iters, float* tflops, void* stream) { return fma_peak_impl(iters, tflops, stream, 1); }
 
 }  // extern "C"
+#endif  // FBP_HOST_EMU

@@ -365,3 +365,131 @@ def test_activation_variant_kernels_emulated_on_cpu_match_oracle(name, tmp_path)
             continue
         e = np.abs(g - rg.numpy()).max() / max(np.abs(rg.numpy()).max(), 1e-30)
         assert e < 2e-5, f"{name} gradient leaf {tuple(g.shape)}: {e:.2e}"
+
+
+def _emu_lib(tmp_path, name):
+    "tests/tools/<name>.cpp (a CUDA source of csrc/ compiled as plain C++ through fbp_host_emu.h) -> ctypes library"
+    import ctypes as C
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / f"lib{name}.so")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(root, "tests", "tools"),
+                        "-I" + os.path.join(root, "fbpinns_b200", "csrc"), "-o", so,
+                        os.path.join(root, "tests", "tools", name + ".cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return C.CDLL(so)
+
+
+def _host_takes_view(takes, n, m_all, m_active):
+    """The kernel-facing view (include/fbpinn_b200.h, fbp_takes_view) of reference-order takes, built with numpy the way
+    csrc/fbp_takes.cu builds it on the device.  Returns (view, arrays kept alive)."""
+    import ctypes as C
+    from fbpinns_b200 import _lib
+    m_take, n_take, p_take, np_take, npou = takes
+    m_take, n_take, p_take, np_take = [np.ascontiguousarray(t, dtype=np.int32) for t in (m_take, n_take, p_take, np_take)]
+    s, q = len(m_take), len(np_take)
+    assert (np.diff(p_take) >= 0).all() and (np.diff(np_take) >= 0).all()
+    perm = np.argsort(m_take, kind="stable")
+    keep = dict(m_take=m_take, np_take=np_take, sub_ids=np.arange(m_all, dtype=np.int32),
+                sub_off=np.concatenate([[0], np.cumsum(np.bincount(m_take, minlength=m_all))]).astype(np.int32),
+                spair_point=n_take[perm].copy(), spair_row=p_take[perm].copy(), spair_sub=m_take[perm].copy(),
+                pos=np.empty(s, dtype=np.int32),
+                row_off=np.searchsorted(p_take, np.arange(q + 1)).astype(np.int32),
+                pt_row_off=np.searchsorted(np_take, np.arange(n + 1)).astype(np.int32))
+    keep["pos"][perm] = np.arange(s, dtype=np.int32)
+    tv = _lib.TakesView()
+    tv.n, tv.s, tv.q, tv.s_active = n, s, q, int(keep["sub_off"][m_active])
+    tv.m_all, tv.m_active, tv.npou = m_all, m_active, int(npou)
+    for field, key in [("d_m_take", "m_take"), ("d_np_take", "np_take"), ("d_sub_ids", "sub_ids"), ("d_sub_off", "sub_off"),
+                       ("d_spair_point", "spair_point"), ("d_spair_row", "spair_row"), ("d_spair_sub", "spair_sub"),
+                       ("d_pos", "pos"), ("d_row_off", "row_off"), ("d_pt_row_off", "pt_row_off")]:
+        setattr(tv, field, keep[key].ctypes.data_as(C.c_void_p))
+    return tv, keep
+
+
+def test_generic_and_streaming_kernels_emulated_on_cpu_match_oracle(tmp_path):
+    """The CUDA sources of the generic family (csrc/fbp_generic.cu) and of the streaming kernels (csrc/fbp_reduce.cu:
+    window sums, row sums, segment-sum + quotient rule and its transpose, Adam) compiled as plain C++ and run on the CPU,
+    chained exactly like a training step: ujs and parameter gradients against the oracle on a reduced Burgers case
+    (fixed + active subdomains, mixed pair counts), one Adam step against the restated optax formula."""
+    import ctypes as C
+    from fbpinns_b200 import configs
+    from fbpinns_b200.engine import Plan
+    from oracle import ref_adam
+    import common
+    gen, red = _emu_lib(tmp_path, "emu_generic"), _emu_lib(tmp_path, "emu_reduce")
+    c = configs.cfg3_burgers(n_sub=(4, 3), n_pts=(17, 13), layer_sizes=(2, 6, 5, 1), line_scheduler=False)
+    active = np.ones(12, dtype=int)
+    active[[2, 7]] = 2                                  # two fixed subdomains: forward only
+    k = common.make_case(c, seed=3, active=active)
+    ui = k.ui
+    jet = k.jets[0]
+    plan = Plan(k.layer_sizes, jet, kernel="generic")
+    P, Cj = plan.P, jet.C
+    all_ims, m_active = np.asarray(ui["all_ims"]), len(ui["active_ims"])
+    x = np.ascontiguousarray(ui["constraints"][0][0], dtype=np.float32)
+    n = x.shape[0]
+    tv, keep = _host_takes_view(ui["takess"][0], n, len(all_ims), m_active)
+    # kernels index the decomposition records and parameter rows by GLOBAL subdomain index through d_sub_ids
+    keep["sub_ids"][:] = all_ims
+    d = k.all_params["static"]["decomposition"]["subdomain"]["params"]
+    f32 = lambda t: np.asarray(t, dtype=np.float32)
+    sub_static = np.ascontiguousarray(np.concatenate([f32(d[0]), f32(d[1]), f32(d[4]), f32(d[5])], axis=1))
+    params = np.ascontiguousarray(np.concatenate([np.concatenate([w.reshape(k.m, -1), b], axis=1) for w, b in k.layers], axis=1), dtype=np.float32)
+    assert params.shape == (k.m, P) and sub_static.shape == (k.m, 2 * k.xd + 3)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    s, q = tv.s, tv.q
+    dsum = np.zeros((q, Cj), np.float32)
+    pair_out = np.full((s, Cj), np.nan, np.float32)
+    scratch = np.zeros(max(plan.scratch_per_pair, 1) * s, np.float32)
+    ujets = np.full((n, Cj), np.nan, np.float32)
+    red.emu_window_sums(plan.handle, C.byref(tv), fp(x), fp(sub_static), fp(dsum))
+    gen.emu_generic_forward(plan.handle, C.byref(tv), fp(x), fp(params), fp(sub_static), fp(pair_out), fp(scratch))
+    red.emu_reduce_forward(plan.handle, C.byref(tv), fp(pair_out), 0, fp(dsum), None, fp(ujets))
+    ref = common.oracle_ujs(k, 0, torch.float64, constrained=False)
+    for (iu, p), r in zip(jet.required_ujs, ref):
+        e = common.rel_err(ujets[:, jet.column(iu, p)], r[:, 0])
+        assert e < 2e-5, f"emulated ujs d{p}: {e:.2e}"
+    # the split used by the multi-GPU halo step gives the same jets
+    nsum = np.zeros((q, Cj), np.float32)
+    ujets2 = np.zeros_like(ujets)
+    red.emu_row_sums(plan.handle, C.byref(tv), fp(pair_out), fp(nsum))
+    red.emu_reduce_forward(plan.handle, C.byref(tv), fp(nsum), 1, fp(dsum), None, fp(ujets2))
+    assert np.array_equal(ujets, ujets2)
+
+    # ---- reverse: cotangent of the jets -> rows -> parameter gradients of the ACTIVE subdomains
+    rng = np.random.default_rng(0)
+    ubar = rng.standard_normal((n, Cj)).astype(np.float32)
+    grow = np.zeros((q, Cj), np.float32)
+    grads = np.zeros((m_active, P), np.float32)
+    red.emu_reduce_backward(plan.handle, C.byref(tv), fp(ubar), fp(dsum), None, fp(grow))
+    gen.emu_generic_backward(plan.handle, C.byref(tv), fp(x), fp(params), fp(sub_static), fp(grow), fp(grads), fp(scratch))
+    decomp_cut = ref_model.cut_decomp(ref_model.to_torch(k.decomp_np, torch.float64), all_ims)
+    lc = [tuple(torch.tensor(t[all_ims], dtype=torch.float64, requires_grad=True) for t in leaf) for leaf in k.layers]
+    ujs = ref_model.fbpinn_forward(decomp_cut, lc, torch.as_tensor(x, dtype=torch.float64), ui["takess"][0], k.jmapss[0])
+    L = sum((torch.tensor(ubar[:, jet.column(iu, p)], dtype=torch.float64) * u[:, 0]).sum() for (iu, p), u in zip(jet.required_ujs, ujs))
+    assert {jet.column(iu, p) for iu, p in jet.required_ujs} == set(range(Cj))
+    rg = torch.autograd.grad(L, [t for leaf in lc for t in leaf])
+    off = 0
+    for t, g in zip([t for leaf in lc for t in leaf], rg):
+        nel = int(np.prod(t.shape[1:]))
+        got = grads[:, off:off + nel].reshape((m_active,) + tuple(t.shape[1:]))
+        e = common.rel_err(got, g.numpy()[:m_active])
+        assert e < 2e-5, f"emulated gradient {tuple(t.shape)}: {e:.2e}"
+        assert float(g[m_active:].abs().max()) > 0            # the fixed subdomains do have a gradient the kernels skip
+        off += nel
+
+    # ---- Adam on the active rows
+    pr, mu, nu = params.copy(), np.zeros_like(params), np.zeros_like(params)
+    rows = np.ascontiguousarray(all_ims[:m_active], dtype=np.int32)
+    count = np.zeros(1, np.int32)
+    red.emu_adam(fp(pr), fp(mu), fp(nu), fp(grads), fp(rows), C.c_int64(m_active), C.c_int64(P), fp(count),
+                 C.c_float(1e-3), C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(0.0))
+    ref_p, _ = ref_adam.adam_update([grads], ref_adam.adam_init([params[rows]]), [params[rows]], learning_rate=1e-3)
+    assert np.allclose(pr[rows], ref_p[0], rtol=2e-6, atol=1e-7)
+    untouched = np.setdiff1d(np.arange(k.m), rows)
+    assert np.array_equal(pr[untouched], params[untouched])

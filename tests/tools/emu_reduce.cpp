@@ -1,0 +1,36 @@
+// CPU emulation of the streaming kernels of fbpinns_b200/csrc/fbp_reduce.cu (window sums, row sums, segment-sum + quotient
+// rule forward and transpose, Adam): their own source compiled as C++ (fbp_host_emu.h), one row / point / element per
+// "thread".  `plan` comes from the real library; every other pointer is a host array.
+#define FBP_HOST_EMU 1
+#include "../../fbpinns_b200/csrc/fbp_reduce.cu"
+
+template <class F>
+static void for_threads(int64_t n, F f) {
+    blockDim.x = 1; gridDim.x = (unsigned)n;
+    for (int64_t t = 0; t < n; ++t) { blockIdx.x = (unsigned)t; threadIdx.x = 0; f(); }
+}
+
+extern "C" int emu_window_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* x, const float* sub_static, float* dsum) {
+    for_threads(tv->q, [&] { window_sums_kernel(plan->dev, *tv, x, sub_static, dsum); });
+    return 0;
+}
+extern "C" int emu_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* pair_out, float* nsum) {
+    for_threads(tv->q, [&] { row_sums_kernel(plan->dev, *tv, pair_out, nsum); });
+    return 0;
+}
+extern "C" int emu_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* pair_out_or_rows, int from_rows,
+                                  const float* dsum, const float* aff, float* ujets) {
+    if (from_rows) for_threads(tv->n, [&] { reduce_forward_kernel<true>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets); });
+    else for_threads(tv->n, [&] { reduce_forward_kernel<false>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets); });
+    return 0;
+}
+extern "C" int emu_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* ubar, const float* dsum,
+                                   const float* aff, float* grow) {
+    for_threads(tv->q, [&] { reduce_backward_kernel(plan->dev, *tv, ubar, dsum, aff, grow); });
+    return 0;
+}
+extern "C" int emu_adam(float* params, float* mu, float* nu, const float* grads, const int32_t* row_ids, int64_t n_rows,
+                        int64_t row_len, const int32_t* count, float lr, float b1, float b2, float eps, float eps_root) {
+    for_threads(n_rows * row_len, [&] { adam_kernel(params, mu, nu, grads, row_ids, n_rows, row_len, count, lr, b1, b2, eps, eps_root); });
+    return 0;
+}

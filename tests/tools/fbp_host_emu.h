@@ -18,6 +18,8 @@ inline cudaError_t cudaGetLastError() { return 0; }
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __shared__ static
+inline void __syncthreads() {}
 
 struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
 static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
