@@ -108,7 +108,10 @@ int fbp_plan_create(fbp_plan** out, const fbp_plan_desc* d) {
     {   // instance validated on B200 (profiles/r1f_tc_bringup.md): two second-order axes, C = 5 (cfg 5)
         const char* e = getenv("FBP_TC_AUTO");
         p->tc_auto = p->tc_ok && p->fast.na2 == 2 && p->fast.na1 == 0 && !(e && e[0] == '0');
-        p->tc_auto_bwd = e && strcmp(e, "full") == 0;
+        // the tensor reverse kernel is part of auto mode since the round-2 timing run (profiles/r2a_tc_bringup.md:
+        // tensor forward v2 without cache stores 1.38 ms + tensor reverse 5.21 ms beat 1.72 + 5.26 ms);
+        // FBP_TC_AUTO=fwd keeps the tiled reverse kernel with the activation cache
+        p->tc_auto_bwd = !(e && strcmp(e, "fwd") == 0);
     }
     p->mode = 0;
     *out = p;

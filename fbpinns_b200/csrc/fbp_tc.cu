@@ -217,7 +217,9 @@ static int tc_forward_v2(FastArgs a, int grid, cudaStream_t st) {
 
 template <class CF>
 static int tc_forward_one(const FastArgs& a, int grid, cudaStream_t st) {
-    if (env_int("FBP_TC_FWD", 1) == 2) return tc_forward_v2<CF>(a, grid, st);     // pipelined variant (bring-up)
+    // the software-pipelined kernel is the default since it was timed (1.383 vs 1.716 ms without cache stores, 1.721 vs
+    // 1.996 ms with them, cfg 5, profiles/r2a_tc_bringup.md); FBP_TC_FWD=1 selects the first kernel
+    if (env_int("FBP_TC_FWD", 2) == 2) return tc_forward_v2<CF>(a, grid, st);
     // 4 warpgroups measured faster than 2 (1.995 vs 2.238 ms on cfg 5, profiles/r1f_tc_bringup.md)
     if (env_int("FBP_TC_NWG", 4) == 2) return tc_forward_nwg<CF, 2>(a, grid, st);
     return tc_forward_nwg<CF, 4>(a, grid, st);

@@ -3,8 +3,7 @@ fbpinns/networks.py:70-194) on the generic kernel family's activation variants (
 oracle: unconstrained ujs and the gradients of every parameter leaf (weights, biases, activation parameters) for a
 random cotangent, 1e-5 relative.
 
-The kernels were written after round 1's GPU budget was spent: the tests run when FBP_ACT_TESTS=1 is set (first hardware
-session of the next round).  Their maths is checked on the CPU (tests/test_oracle_and_math.py::
+First run on a B200 in round 2 (5 passed, profiles/r2a_tc_bringup.md); unconditional since.  Their maths is checked on the CPU (tests/test_oracle_and_math.py::
 test_activation_jet_formulas_match_autograd) and the oracle / host mirrors against the reference's own network_fn
 (tests/test_golden_reference.py::test_network_plugins_match_reference_source)."""
 import os
@@ -20,8 +19,7 @@ from fbpinns_b200.trainers import get_update_inputs
 from oracle import ref_model
 import common
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FBP_ACT_TESTS", "0") != "1", reason="set FBP_ACT_TESTS=1 (bring-up of the network plug-ins)")]
+pytestmark = [pytest.mark.gpu]
 
 TOL = 1e-5
 NETS = {"fcn": (N.FCN, "fcn", 0), "adaptive_fcn": (N.AdaptiveFCN, "adaptive_fcn", 1), "siren": (N.SIREN, "siren", 0),

@@ -41,6 +41,34 @@ def test_adam_kernel_matches_restated_optax():
         assert int(adam.count.item()) == it + 1 == int(st["count"])
 
 
+def test_adam_kernel_matches_torch_optim_adam_50_steps():
+    """A10 pin: fbp_adam_step against torch.optim.Adam (CPU float32/float64), an implementation independent of the
+    oracle's restatement, 50 steps, gradients over six decades, a row that joins the active set at step 20 (zero
+    moments, global count — fbpinns/trainers.py:51-60, 528-531)."""
+    from test_oracle_and_math import _torch_adam_run
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    m, P, steps, join = 5, 41, 50, 20
+    p0 = rng.normal(size=(m, P)).astype(np.float32)
+    grads = [(rng.normal(size=(m, P)) * 10.0 ** rng.integers(-3, 3, size=(m, 1))).astype(np.float32) for _ in range(steps)]
+    early, late = np.array([0, 2, 3], np.int32), np.array([0, 1, 2, 3], np.int32)      # row 1 joins late, row 4 never
+    want64 = _torch_adam_run([p0[i] for i in range(m)], [[g[i] for i in range(m)] for g in grads],
+                             [0, join, 0, 0, steps + 1], torch.float64)
+    want32 = _torch_adam_run([p0[i] for i in range(m)], [[g[i] for i in range(m)] for g in grads],
+                             [0, join, 0, 0, steps + 1], torch.float32)
+    params = torch.as_tensor(p0.copy(), device=dev)
+    adam = PackedAdam(m, P, 0, dev, learning_rate=1e-3)
+    for it in range(steps):
+        rows = early if it < join else late
+        adam.step(params, torch.as_tensor(grads[it][rows], device=dev), torch.as_tensor(rows, device=dev))
+    got = params.cpu().numpy()
+    assert int(adam.count.item()) == steps
+    assert np.array_equal(got[4], p0[4])
+    for i in range(4):
+        assert np.max(np.abs(got[i] - want64[i])) <= 3e-6 * max(1.0, np.max(np.abs(want64[i]))), i
+        assert np.max(np.abs(got[i] - want32[i])) <= 3e-6 * max(1.0, np.max(np.abs(want32[i]))), i
+
+
 def _oracle_curve(k, n_steps, dtype):
     ui = k.ui
     decomp_cut = ref_model.cut_decomp(ref_model.to_torch(k.decomp_np, dtype), ui["all_ims"])

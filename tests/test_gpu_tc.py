@@ -1,10 +1,8 @@
 """GPU parity of the tcgen05 ("tensor") kernel family (fbpinns_b200/csrc/fbp_tc*.cuh): 3xTF32 hidden-layer GEMMs on the
 tensor cores must stay inside the same 1e-5 bar as the FP32 kernels.
 
-What has already run on a B200 (profiles/r1f_tc_bringup.md) is tested unconditionally: the MMA self-test and the
-forward kernel of the cfg 5 instance, which `kernel="auto"` uses.  The instances and variants that have only been
-checked through tests/tools/tc_capi_check.py (other jet sets, the pipelined forward, the reverse kernel) run when
-FBP_TC_TESTS=1 is set — the first hardware session of the next round — and stay opt-in until then."""
+Everything runs unconditionally since the round-2 hardware session (profiles/r2a_tc_bringup.md): the MMA self-test, every
+forward instance, both forward kernels (FBP_TC_FWD=1 | 2) and the reverse kernel (`kernel="tensor-full"`)."""
 import os
 
 import numpy as np
@@ -16,7 +14,6 @@ from fbpinns_b200.engine import unpack_params
 import common
 
 pytestmark = pytest.mark.gpu
-bringup = pytest.mark.skipif(os.environ.get("FBP_TC_TESTS", "0") != "1", reason="set FBP_TC_TESTS=1 (bring-up of the opt-in variants)")
 
 TOL = 1e-5
 
@@ -45,7 +42,7 @@ def test_mma_selftest_single_pass_is_tf32_accurate():
     assert 1e-6 < err < 3e-3, f"single-pass TF32: error {err:.2e}"
 
 
-@pytest.mark.parametrize("name", [pytest.param("cfg2", marks=bringup), "cfg5"])
+@pytest.mark.parametrize("name", ["cfg2", "cfg5"])
 def test_tensor_forward_matches_oracle_and_tiled(name):
     import gpu_common
     cases = [dict(configs.SMALL[name])]                   # the size the oracle-level tests of the other families use
@@ -73,7 +70,6 @@ def test_tensor_forward_matches_oracle_and_tiled(name):
             assert common.rel_err(ev_t.cache.cpu().numpy(), ev_f.cache.cpu().numpy()) < 5e-6
 
 
-@bringup
 @pytest.mark.parametrize("kernel", ["tensor", "tensor-full"])
 @pytest.mark.parametrize("name", ["cfg2", "cfg5"])
 def test_tensor_loss_and_grads_match_oracle(name, kernel):
@@ -95,7 +91,6 @@ def test_tensor_loss_and_grads_match_oracle(name, kernel):
         assert ew < TOL and eb < TOL, f"{name} layer {l}: grad rel err W {ew:.2e} b {eb:.2e}"
 
 
-@bringup
 def test_tensor_reverse_matches_tiled_with_partial_tiles_and_fixed_subdomains():
     """tensor-full vs tiled gradients on a case with full tiles, partial tails and fixed (forward-only) subdomains"""
     import gpu_common
@@ -120,7 +115,6 @@ def test_tensor_reverse_matches_tiled_with_partial_tiles_and_fixed_subdomains():
         assert common.rel_err(grads["tensor-full"], grads["tiled"]) < 5e-6
 
 
-@bringup
 def test_tensor_training_curve_matches_tiled():
     "30 Adam steps of the reduced cfg 5 with either family: same loss curve within 1e-4 relative"
     from fbpinns_b200.trainers import FBPINNTrainer
@@ -135,3 +129,19 @@ def test_tensor_training_curve_matches_tiled():
     for kernel in ["tensor", "tensor-full"]:
         b = np.array(losses[kernel])
         assert np.all(np.abs(a - b) <= 1e-4 * np.abs(a)), (kernel, a[-3:], b[-3:])
+
+
+def test_both_forward_kernels_agree(monkeypatch):
+    "FBP_TC_FWD=1 (first kernel) and the default software-pipelined kernel: same pair outputs and activation cache"
+    import gpu_common
+    k = common.make_case(configs.cfg5_poisson(n_sub=(5, 4), n_pts=(160, 136)), seed=0)
+    outs = {}
+    for v in ("1", "2"):
+        monkeypatch.setenv("FBP_TC_FWD", v)
+        dd, inp, params = gpu_common.device_case(k, kernel="tensor")
+        ev = inp.evaluators[0]
+        u = ev.forward(params)
+        torch.cuda.synchronize()
+        outs[v] = (u.cpu().numpy(), ev.cache.cpu().numpy())
+    assert common.rel_err(outs["1"][0], outs["2"][0]) < 5e-6
+    assert common.rel_err(outs["1"][1], outs["2"][1]) < 5e-6

@@ -201,13 +201,16 @@ def test_every_baseline_config_has_a_tiled_kernel_instance():
 
 
 def test_tensor_family_selection(monkeypatch):
-    """which plans get the tcgen05 family: only H = 32 with two hidden layers and C <= 5; `auto` picks it for the instance
-    validated on hardware (cfg 5's jets) unless FBP_TC_AUTO=0; asking for it on other plans falls back to auto"""
+    """which plans get the tcgen05 family: only H = 32 with two hidden layers and C <= 5; `auto` picks it (forward and reverse) for the
+    instance timed on hardware (cfg 5's jets) unless FBP_TC_AUTO=0 (tiled) or =fwd (tensor forward, tiled reverse); asking for it on other plans falls back to auto"""
     from fbpinns_b200.engine import Plan
     poisson = JetSpec(((0, (0, 0)), (0, (1, 1))), 2, 1)
     monkeypatch.delenv("FBP_TC_AUTO", raising=False)
     p = Plan([2, 32, 32, 1], poisson)
-    assert p.has_tensor and p.kernel == "auto" and p.forward_family == "tensor" and p.cache_per_pair == 32 * 5
+    assert p.has_tensor and p.kernel == "auto" and p.forward_family == "tensor" and p.cache_per_pair == 0   # tensor reverse too
+    monkeypatch.setenv("FBP_TC_AUTO", "fwd")
+    assert Plan([2, 32, 32, 1], poisson).cache_per_pair == 32 * 5        # tensor forward + tiled reverse with the cache
+    monkeypatch.delenv("FBP_TC_AUTO")
     p.set_kernel("tiled")
     assert p.forward_family == "tiled"
     p.set_kernel("tensor-full")

@@ -493,3 +493,49 @@ def test_generic_and_streaming_kernels_emulated_on_cpu_match_oracle(tmp_path):
     assert np.allclose(pr[rows], ref_p[0], rtol=2e-6, atol=1e-7)
     untouched = np.setdiff1d(np.arange(k.m), rows)
     assert np.array_equal(pr[untouched], params[untouched])
+
+
+# --------------------------------------------------------------------------------------------------- Adam vs an independent implementation
+
+def _torch_adam_run(p0_list, grads_per_step, join_step, dtype, lr=1e-3):
+    """torch.optim.Adam (an implementation independent of the oracle's restatement: m / (sqrt(v)/sqrt(bc2) + eps) * lr/bc1)
+    driven like the reference drives optax: ONE global step count; a parameter that joins the active set at `join_step`
+    starts with zero moments but the global count (fbpinns/trainers.py:51-60, 528-531, 640)."""
+    ps = [torch.tensor(p, dtype=dtype, requires_grad=True) for p in p0_list]
+    opts = [torch.optim.Adam([p], lr=lr, betas=(0.9, 0.999), eps=1e-8) for p in ps]
+    for it, grads in enumerate(grads_per_step):
+        for i, (p, g, opt) in enumerate(zip(ps, grads, opts)):
+            if it < join_step[i]:
+                continue
+            if it == join_step[i] and it > 0:       # late joiner: zero moments, global count
+                opt.state[p]["step"] = torch.tensor(float(it))
+                opt.state[p]["exp_avg"] = torch.zeros_like(p)
+                opt.state[p]["exp_avg_sq"] = torch.zeros_like(p)
+            p.grad = torch.as_tensor(g, dtype=dtype)
+            opt.step()
+    return [p.detach().numpy() for p in ps]
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 3e-6)])
+def test_oracle_adam_matches_torch_optim_adam_50_steps(dtype, tol):
+    """A10 pin: optax is absent from the reference tree, so the oracle's Adam is cross-checked against an independent
+    implementation of the same published update (torch.optim.Adam, CPU) over 50 steps with gradients spanning six
+    decades, including a subdomain that joins the active set late."""
+    from oracle import ref_adam
+    rng = np.random.default_rng(5)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    p0 = [rng.normal(size=(4, 9)).astype(npdt), rng.normal(size=(3,)).astype(npdt)]
+    join = [0, 20]
+    steps = 50
+    grads = [[(rng.normal(size=p.shape) * 10.0 ** rng.integers(-3, 3)).astype(npdt) for p in p0] for _ in range(steps)]
+    want = _torch_adam_run(p0, grads, join, dtype)
+    # oracle: the late joiner is held out of the tree, then merged with zero moments and the global count
+    params, st = [p0[0].copy()], ref_adam.adam_init([p0[0]])
+    for it in range(steps):
+        if it == join[1]:
+            params.append(p0[1].copy())
+            st = dict(count=st["count"], mu=st["mu"] + [np.zeros_like(p0[1])], nu=st["nu"] + [np.zeros_like(p0[1])])
+        params, st = ref_adam.adam_update(grads[it][:len(params)], st, params, learning_rate=1e-3)
+    assert int(st["count"]) == steps
+    for a, b in zip(params, want):
+        assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b))), np.max(np.abs(a - b))
