@@ -83,7 +83,7 @@ SIGNATURES = {
     "fbp_fma_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
     "fbp_ffma2_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
     "fbp_tc_selftest": (C.c_int, [_P, _P, _P, _I32, _P]),
-    "fbp_tc_selftest_mn": (C.c_int, [_P, _P, _P, _I32, _P]),
+    "fbp_tc_selftest_g": (C.c_int, [_P, _P, _P, _I32, _P]),
 }
 
 _lib = None

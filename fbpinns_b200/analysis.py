@@ -32,9 +32,18 @@ def FBPINN_model(c, all_params, active, x_batch, device=None):
     params = pack_params(plan, layers)
     with torch.no_grad():
         u = ev.forward(params)
-        ap = {"static": {k: {kk: (v.to(dev) if torch.is_tensor(v) else v) for kk, v in d.items() if kk != "_device_cache"}
-                         for k, d in all_params["static"].items() if k != "decomposition"},
-              "trainable": {k: v for k, v in all_params["trainable"].items() if k != "network"}}
+        # the reference hands the FULL tree to constraining_fn (fbpinns/trainers.py:173); tensors / numpy leaves of the
+        # static problem and domain entries go to the device, the kernels' private cache entry is dropped
+        def dev_tree(d):
+            if isinstance(d, dict):
+                return {k: dev_tree(v) for k, v in d.items() if k != "_device_cache"}
+            if torch.is_tensor(d):
+                return d.to(dev)
+            if isinstance(d, np.ndarray) and d.dtype.kind == "f":
+                return torch.as_tensor(d, dtype=torch.float32, device=dev)
+            return d
+        ap = {"static": {k: (dev_tree(d) if k in ("problem", "domain") else d) for k, d in all_params["static"].items()},
+              "trainable": {k: (dev_tree(v) if k == "problem" else v) for k, v in all_params["trainable"].items()}}
         u = c.problem.constraining_fn(ap, x, u)
         wp = ev.dsum[:takes.q, 0:1].clone()
         us = ev.pair_values_reference_order()

@@ -1,5 +1,5 @@
 // tcgen05 ("tensor") kernel family: instantiations, launch glue and the MMA self-test.
-#include "fbp_tc_bwd.cuh"
+#include "fbp_tc_bwd2.cuh"
 
 using namespace fbptc;
 
@@ -106,67 +106,73 @@ extern "C" int fbp_tc_selftest(const float* d_a, const float* d_w, float* d_out,
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// Self-test of the MN-major shared-memory operand form the planned tensor-core weight gradient needs:
-// out[128][64] = sum_p A[p][m] * B[p][n] over 128 "points" p, A (128 x 128) and B (128 x 64) staged row-by-row (one
-// thread = one p, as the point warps would) in the canonical MN-major no-swizzle layout, both operands from shared
-// memory (".ss" form), 16 MMAs with M = 128, N = 64, K = 8.  Inputs are rounded to TF32 so that one pass is exact up to
-// FP32 accumulation.  variant bit 0: swap LBO and SBO.
+// Self-test of the operand form of the tensor-core weight gradient (fbp_tc_bwd2.cuh): BOTH operands from shared memory
+// (".ss"), contraction over the 128 "points" p of a tile:  out[m][n] = sum_p A[p][m] * B[p][n],  m < 128 (a stack of four
+// 32-row images), n < 32.  The operands are staged exactly as the point warps do it: thread = point, one image row per
+// store, K-major no-swizzle core matrices with the K step padded to GK_LBO = 144 bytes (conflict-free 32-lane stores),
+// one slot per quarter tile (32 points = 4 MMAs of K = 8), accumulation over the four quarters in tensor memory.
+// Inputs are rounded to TF32 so that one pass is exact up to FP32 accumulation.
+//   variant bit 0: swap LBO and SBO     bit 1: unpadded K step (LBO 128, SBO 1024)
+//   bit 2: M = 64 (only the first 64 rows of A take part; the caller maps accumulator rows to tensor-memory lanes)
 // -----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) tc_selftest_mn_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                                float* __restrict__ out, int variant) {
-    extern __shared__ __align__(128) float smn[];
-    float* as = smn;                      // 128 x 128
-    float* bs = smn + 128 * 128;          // 128 x 64
+__global__ void __launch_bounds__(128, 1) tc_selftest_g_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               float* __restrict__ out, int variant) {
+    extern __shared__ __align__(128) float sg[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = warp_uniform();
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    for (int m = 0; m < 128; ++m) as[mncore_index(m, tid, 128)] = __uint_as_float(tf32_rn(A[tid * 128 + m]));
-    for (int n = 0; n < 64; ++n) bs[mncore_index(n, tid, 64)] = __uint_as_float(tf32_rn(B[tid * 64 + n]));
+    const uint32_t lbo = (variant & 2) ? 128u : GK_LBO, sbo = 8u * lbo;
+    const int img = 4 * (int)sbo / 4;                      // floats per 32-row image of one quarter
+    const int slot = 5 * img;                              // 4 A images + 1 B image per quarter
+    const int q = tid >> 5, pq = tid & 31;                 // quarter and point inside it
+    for (int m = 0; m < 128; ++m)
+        sg[q * slot + (m >> 5) * img + gk_index(m & 31, pq, lbo)] = __uint_as_float(tf32_rn(A[tid * 128 + m]));
+    for (int n = 0; n < 32; ++n) sg[q * slot + 4 * img + gk_index(n, pq, lbo)] = __uint_as_float(tf32_rn(B[tid * 32 + n]));
     if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
     __syncthreads();
-    if (warp == 0) tmem_alloc(&tmem_slot, 64);
+    if (warp == 0) tmem_alloc(&tmem_slot, 32);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_slot;
     if (warp == 0 && elect_one()) {
-        const uint32_t a_lbo = (variant & 1) ? MN_SBO : mn_lbo(128), a_sbo = (variant & 1) ? mn_lbo(128) : MN_SBO;
-        const uint32_t b_lbo = (variant & 1) ? MN_SBO : mn_lbo(64), b_sbo = (variant & 1) ? mn_lbo(64) : MN_SBO;
-        const uint64_t ad = make_smem_desc(smem_u32(as), a_lbo, a_sbo), bd = make_smem_desc(smem_u32(bs), b_lbo, b_sbo);
-        constexpr uint32_t idesc = make_idesc_tf32(128, 64, 1, 1);
-        for (int ks = 0; ks < 16; ++ks)     // one K group of 8 points per MMA: the next group starts LBO bytes further
-            mma_tf32_ss(tbase, ad + (uint64_t)((ks * mn_lbo(128)) >> 4), bd + (uint64_t)((ks * mn_lbo(64)) >> 4), idesc, ks != 0);
+        const uint32_t idesc = (variant & 4) ? make_idesc_tf32(64, 32) : make_idesc_tf32(128, 32);     // bit 2: M = 64
+        const uint32_t dl = (variant & 1) ? sbo : lbo, ds = (variant & 1) ? lbo : sbo;
+        for (int qq = 0; qq < 4; ++qq) {
+            const uint64_t ad = make_smem_desc(smem_u32(sg + qq * slot), dl, ds);
+            const uint64_t bd = make_smem_desc(smem_u32(sg + qq * slot + 4 * img), dl, ds);
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 2 * lbo) >> 4);
+                mma_tf32_ss(tbase, ad + adv, bd + adv, idesc, (qq | ks) != 0);
+            }
+        }
         mma_commit(&bar);
     }
     mbar_wait_or_trap(&bar, 0);
     tc_fence_after();
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
+    for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[8];
         tmem_ld8(tbase + lane_base + 8 * ch, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 8; ++e) out[tid * 64 + 8 * ch + e] = __uint_as_float(v[e]);
+        for (int e = 0; e < 8; ++e) out[tid * 32 + 8 * ch + e] = __uint_as_float(v[e]);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 64);
+    if (warp == 0) tmem_dealloc(tbase, 32);
 }
 
-extern "C" int fbp_tc_selftest_mn(const float* d_a, const float* d_b, float* d_out, int32_t variant, void* stream) {
-    FBP_REQUIRE(d_a && d_b && d_out, "fbp_tc_selftest_mn: null buffer");
-    constexpr int bytes = (128 * 128 + 128 * 64) * 4;
-    static bool configured = false;
-    if (!configured) {
-        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_selftest_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        configured = true;
-    }
-    tc_selftest_mn_kernel<<<1, 128, bytes, (cudaStream_t)stream>>>(d_a, d_b, d_out, variant);
+extern "C" int fbp_tc_selftest_g(const float* d_a, const float* d_b, float* d_out, int32_t variant, void* stream) {
+    FBP_REQUIRE(d_a && d_b && d_out, "fbp_tc_selftest_g: null buffer");
+    constexpr int bytes = 4 * 5 * 8 * (int)GK_LBO * 4;     // 4 quarters x 5 images x 4 row groups x 8 K cores
+    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_selftest_g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    tc_selftest_g_kernel<<<1, 128, bytes, (cudaStream_t)stream>>>(d_a, d_b, d_out, variant);
     FBP_LAUNCH_CHECK();
     return 0;
 }
@@ -191,11 +197,9 @@ static int env_int(const char* name, int dflt) {
 template <class CF, int NWG>
 static int tc_forward_nwg(FastArgs a, int grid, cudaStream_t st) {
     constexpr size_t bytes = sizeof(float) * FwdSmem<CF, NWG>::FLOATS;
-    static bool configured = false;
-    if (!configured) {
-        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<CF, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = true;
-    }
+    // the attribute belongs to the (function, device) pair and the call is cheap: set it on every launch, so that a
+    // process driving several GPUs configures each of them
+    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<CF, NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     a.dbg = env_int("FBP_TC_DEBUG", 0);
     tc_forward_kernel<CF, NWG><<<grid, 128 * NWG, bytes, st>>>(a);
     FBP_LAUNCH_CHECK();
@@ -205,11 +209,9 @@ static int tc_forward_nwg(FastArgs a, int grid, cudaStream_t st) {
 template <class CF>
 static int tc_forward_v2(FastArgs a, int grid, cudaStream_t st) {
     constexpr size_t bytes = sizeof(float) * FwdSmem<CF, 4>::FLOATS;
-    static bool configured = false;
-    if (!configured) {
-        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel2<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = true;
-    }
+    // the attribute belongs to the (function, device) pair and the call is cheap: set it on every launch, so that a
+    // process driving several GPUs configures each of them
+    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel2<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     tc_forward_kernel2<CF><<<grid, 512, bytes, st>>>(a);
     FBP_LAUNCH_CHECK();
     return 0;
@@ -242,18 +244,38 @@ template <class CF>
 static int tc_backward_one(FastArgs a, int grid, cudaStream_t st) {
     constexpr size_t bytes = sizeof(float) * BwdSmem<CF>::FLOATS;
     static_assert(bytes <= 227 * 1024, "reverse kernel: shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = true;
-    }
+    // the attribute belongs to the (function, device) pair and the call is cheap: set it on every launch, so that a
+    // process driving several GPUs configures each of them
+    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     a.dbg = env_int("FBP_TC_DEBUG", 0);
     tc_backward_kernel<CF><<<grid, BWD_NT, bytes, st>>>(a);
     FBP_LAUNCH_CHECK();
     return 0;
 }
 
+// second generation: weight gradient on the tensor core (fbp_tc_bwd2.cuh)
+template <class CF>
+static int tc_backward_two(FastArgs a, int grid, cudaStream_t st) {
+    constexpr size_t bytes = sizeof(float) * Bwd2Cfg<CF>::FLOATS;
+    static_assert(bytes <= 226 * 1024, "reverse kernel 2: shared memory budget");
+    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel2<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    a.dbg = env_int("FBP_TC_DEBUG", 0);
+    tc_backward_kernel2<CF><<<grid, B2_NT, bytes, st>>>(a);
+    FBP_LAUNCH_CHECK();
+    return 0;
+}
+
 int fbp_tc_backward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st) {
+    if (env_int("FBP_TC_BWD", 1) == 2) {
+        switch (f.na2 * 4 + f.na1) {
+            case 0: return tc_backward_two<FastCfg<32, 2, 0, 0>>(a, grid, st);
+            case 1: return tc_backward_two<FastCfg<32, 2, 0, 1>>(a, grid, st);
+            case 4: return tc_backward_two<FastCfg<32, 2, 1, 0>>(a, grid, st);
+            case 5: return tc_backward_two<FastCfg<32, 2, 1, 1>>(a, grid, st);
+            case 8: return tc_backward_two<FastCfg<32, 2, 2, 0>>(a, grid, st);
+            default: break;
+        }
+    }
     switch (f.na2 * 4 + f.na1) {
         case 0: return tc_backward_one<FastCfg<32, 2, 0, 0>>(a, grid, st);
         case 1: return tc_backward_one<FastCfg<32, 2, 0, 1>>(a, grid, st);

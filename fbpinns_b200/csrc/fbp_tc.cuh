@@ -49,7 +49,8 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
     // base offset [49,52) = 0, lbo mode [52] = 0, layout type [61,64) = 0 (SWIZZLE_NONE)
     return d;
 }
-// instruction descriptor of tcgen05.mma.kind::tf32, FP32 accumulate; a_mn / b_mn = 1: the operand is MN-major
+// instruction descriptor of tcgen05.mma.kind::tf32, FP32 accumulate; a_mn / b_mn = 1: the operand is MN-major (the
+// MN-major form failed its hardware self-test in round 2 and is not used; every operand of the family is K-major)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
     return (1u << 4)                    // [4,6)   D format F32
          | (2u << 7)                    // [7,10)  A format TF32
@@ -59,13 +60,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 
          | ((uint32_t)(M >> 4) << 24);  // [24,29) M >> 4
 }
 
-// canonical MN-major no-swizzle placement of element (mn, k) of an operand with MN rows of the MMA and K = contraction
-// index (floats): core matrices of 8 (K) x 4 (MN) elements stored as 128 contiguous bytes, the MN / 4 cores of one
-// K group contiguous (SBO = 128 B), K groups (8 per MMA) MN * 32 bytes apart (LBO).  Checked against CuTe's
-// Layout_MN_INTER_Atom in tests/tools/umma_desc_check.cu.
-__host__ __device__ constexpr int mncore_index(int mn, int k, int MN) { return (mn & 3) + (k & 7) * 4 + (mn >> 2) * 32 + (k >> 3) * (MN * 8); }
-constexpr uint32_t MN_SBO = 128;
-__host__ __device__ constexpr uint32_t mn_lbo(int MN) { return (uint32_t)MN * 32u; }
+// Operand images of the tensor-core weight gradient (fbp_tc_bwd2.cuh): [32 rows][32 points of a quarter tile], K-major
+// (K = point), no swizzle: 8 x 4 core matrices of 128 contiguous bytes; the 8 cores of a row group are GK_LBO = 144
+// bytes apart along K (16 bytes of padding: the 32 lanes of a warp, which hold the 32 points of one row, then store to
+// 32 different banks), row groups GK_SBO = 8 * 144 bytes apart.  One MMA (K = 8) reads two cores: next K step = +288 B.
+constexpr uint32_t GK_LBO = 144, GK_SBO = 8 * GK_LBO;
+constexpr int GK_IMG = 4 * GK_SBO / 4;                       // floats per 32-row image (1152)
+__host__ __device__ constexpr int gk_index(int row, int k, uint32_t lbo = GK_LBO) {
+    return (row >> 3) * (int)(8 * lbo / 4) + (k >> 2) * (int)(lbo / 4) + (row & 7) * 4 + (k & 3);
+}
 
 // canonical K-major no-swizzle placement of element (row n, column k) of a [rows][32] tf32 matrix, in floats:
 // 8 x 4 core matrices of 32 floats, the 8 cores of a row group contiguous along K (LBO = 128 B), row groups 1024 B apart

@@ -1,0 +1,615 @@
+// tcgen05 ("tensor") family, reverse kernel, second generation: EVERY GEMM of the reverse pass on the tensor core,
+// including the weight gradient of the hidden matrix (the FFMA2 gradient warps of fbp_tc_bwd.cuh were the critical path:
+// 5.21 ms with them, 3.34 ms without, profiles/r2a_tc_bringup.md).
+//
+//   warps 0-7  "point warps": thread (g, p) = point row p of the 128-pair tile (= TMEM lane), hidden units [16 g, 16 g + 16)
+//   warp  8    "MMA warp":    one elected lane issues every tcgen05.mma of the CTA, driven by mbarriers
+//   (warps 9-11 complete the third warpgroup: setmaxnreg moves its registers to the point warps, 56 vs 224 per thread)
+//
+// The first layer is linear in the normalised point, so its jets factor per unit k:  h1_0 = t,  h1_s = g kappa_s[k],
+// h1_ss = -2 kappa_s[k]^2 (t g)   with t = tanh(a0), g = 1 - t^2, kappa_s[k] = W0[k][axis s] / sd.  That is used three times:
+//   MMA 1   a2 = h1 W1^T       A operands (tensor memory, hi/lo): t, g kappa_s, t g      B: W1 and W1 diag(-2 kappa_s^2)
+//   MMA 3   hbar1 = abar2 W1   A operands: abar2 (C components, hi/lo)   B: W1^T, diag(kappa_s) W1^T, diag(-2 kappa_s^2) W1^T
+//           accumulated into THREE blocks  D_t, D_g, D_tg  so that  abar0 = g D_t - 2 t g D_g + g (1 - 3 t^2) D_tg
+//   G       the weight gradient contracts over POINTS (= TMEM lanes), so both operands come from shared memory:
+//           G_t = abar2_0^T t,  G_g[s] = abar2_s^T g,  G_tg[s] = abar2_ss^T (t g)     (raw products, 32 x 32 each), then
+//           W1bar[j][k] = G_t + sum_s kappa_s[k] G_g[s] - 2 sum_s kappa_s[k]^2 G_tg[s]                    (end of item)
+//           kappa_bar_s[k] = sum_j W1[j][k] (G_g[s][j][k] - 4 kappa_s[k] G_tg[s][j][k])   -> the derivative path of W0bar
+//           The point threads write hi/lo images of abar2 and (t, g, t g) for their quarter tile (32 points) into a ring
+//           slot in shared memory (K-major, K = point, padded K step: conflict-free 32-lane stores, fbp_tc.cuh GK_*);
+//           the hi/lo images of two components are stacked on M = 128 rows, so that ONE accumulation
+//           [x_hi; y_hi; x_lo; y_lo] (g_hi + g_lo) carries the whole 3xTF32 product (the fourth term lo*lo is harmless);
+//           The tensor core accumulates with truncation, which shows after a few hundred chained MMAs (measured: 9e-6 of the
+//           largest gradient entry against 2.5e-6 for the FP32 kernels when G stayed in tensor memory for a whole work
+//           item), so every tile starts fresh accumulators (32 chained MMAs) and the point threads add the previous
+//           tile's G into registers (round to nearest) while the tensor core works on the next one.
+//
+// TMEM columns (C = 5):  [0,320) A operands (MMA 1 uses 256 of them, MMA 3 all), D1 = a2 at [256,416) (its first 64 columns
+// alias the lo parts of abar2's last two components: only ever touched by the thread that owns the same lane and units,
+// read before written), D3 at [320,416), G at [416,512).
+// Shared memory: parameters 9 KB, B operands (3 + 5 variants, hi/lo) 64 KB, two ring slots of 72 KB.
+#pragma once
+#include "fbp_tc_bwd.cuh"
+
+namespace fbptc {
+
+constexpr int B2_NPW = 8;                 // point warps
+constexpr int B2_NPT = B2_NPW * 32;       // 256 point threads
+constexpr int B2_NT = B2_NPT + 128;       // + the MMA warpgroup (warp 8 issues, warps 9-11 only help at the end of the item)
+constexpr uint32_t COL_G = 416;           // G_g, G_tg, G_t: 32 columns each
+
+template <class CF>
+struct Bwd2Cfg {
+    static constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
+    static constexpr int CA1 = 1 + NS + (NA2 > 0 ? 1 : 0);      // A operands of MMA 1: t, g kappa_s, t g
+    static constexpr int NB1 = 1 + NA2;                         // B variants of MMA 1
+    static constexpr int NB2 = 1 + NS + NA2;                    // B variants of MMA 3
+    static constexpr uint32_t COL_A1LO = CA1 * 32, COL_A3LO = C * 32;
+    static constexpr uint32_t COL_D1 = 2 * CA1 * 32, COL_D3 = 2 * C * 32;
+    static_assert(COL_D1 + C * 32 <= COL_G && COL_D3 + 96 <= COL_G, "tensor memory budget");
+    static constexpr int OFF_B1 = (CF::SM_PARAMS + 31) & ~31;   // [NB1][hi, lo][H*H]   B1_v[n = j][k] = W1[j][k] sc_v[k]
+    static constexpr int OFF_B2 = OFF_B1 + NB1 * 2 * H * H;     // [NB2][hi, lo][H*H]   B2_v[n = k][j] = W1[j][k] sc_v[k]
+    static constexpr int OFF_RING = OFF_B2 + NB2 * 2 * H * H;
+    static constexpr int NIMG = 16;
+    static constexpr int SLOT = NIMG * GK_IMG;                  // floats per ring slot (one quarter tile)
+    static constexpr int FLOATS = OFF_RING + 2 * SLOT;
+    // ring images (32 rows x 32 points each); the stacks of one MMA are contiguous
+    static constexpr int img_ag(int part, int s) { return part * 2 + s; }        // first-order abar2 of slot s
+    static constexpr int img_atg(int part, int s) { return 4 + part * 2 + s; }   // second-order abar2 of slot s
+    static constexpr int img_at(int part) { return 8 + part; }                   // value abar2 (the M = 128 MMA also reads 10, 11)
+    static constexpr int img_phi(int f, int part) { return 10 + 2 * f + part; }  // f: 0 t, 1 g, 2 t g
+    // end-of-item scratch (floats, over the ring)
+    static constexpr int RED_GD = 0;                            // [128 lanes][96]
+    static constexpr int RED_L0 = SLOT;                         // [8 warps][2][32]
+    static constexpr int RED_WL = RED_L0 + B2_NPW * 2 * 32;     // [16][256]
+    static constexpr int RED_B1 = RED_WL + 16 * B2_NPT;         // [16][256]
+    static constexpr int RED_BL = RED_B1 + 16 * B2_NPT;         // [8]
+    static constexpr int RED_KB = RED_BL + 8;                   // [max(NS,1)][32]
+    static_assert(128 * 96 <= SLOT && RED_KB + 2 * 32 <= 2 * SLOT, "reduction scratch must fit the ring");
+};
+
+// hi = the value itself (the tensor core reads only the upper 19 bits), lo = what that read drops
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// 3xTF32 product of one 128 x 32 A block in tensor memory with N rows of B (canonical layout; N = 32: one matrix, N = 64:
+// two matrices stored back to back), small terms first; `fresh`: the first MMA overwrites the accumulator.  One
+// instruction per K step and product (12 in all): the single issuing thread, not the tensor pipe, is what N = 16 halves
+// would saturate.
+template <int N>
+__device__ __forceinline__ void issue_gemm_acc(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, N);
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) {
+        const uint32_t acol = (pr == 0) ? a_lo : a_hi;
+        const uint64_t bd = (pr == 1) ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            mma_tf32_ts(d_tmem, acol + ks * 8, bd + (uint64_t)((ks * 2 * B_LBO) >> 4), idesc, (fresh && pr == 0 && ks == 0) ? 0u : 1u);
+    }
+}
+
+template <class CF>
+__global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
+    static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");
+    using L = Bwd2Cfg<CF>;
+    constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1, CA1 = L::CA1;
+    constexpr int HH = H * H;
+
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t bar_a1, bar_a3, bar_m1, bar_m3, bar_full[2], bar_free[2], bar_gtile;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;
+    // a.dbg (timing experiments only, results are then wrong): 1 = no weight-gradient staging / G MMAs, 4 = no ring stores
+    // (the G MMAs run on stale images), 8 = no G MMA issue (the stores happen), 32 = no butterfly
+    const int dbg = a.dbg;
+
+    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
+    const int im = a.sub_ids[sp];
+    const int xd = a.xd;
+    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (d < xd) {
+            const float lo = ss[d], hi = ss[xd + d];
+            mu[d] = (hi + lo) * 0.5f;
+            isd[d] = 1.0f / ((hi - lo) * 0.5f);
+        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
+    }
+    const float flag = ss[2 * xd], un_sd = ss[2 * xd + 2];
+    const float* prow = a.params + (int64_t)im * a.P;
+    fast_load_params<CF, B2_NT>(sm, prow, xd, isd, a.axis, false);
+    __syncthreads();
+    {   // B operands: W1 and its scaled variants, hi/lo, canonical K-major layout
+        const float* w1 = prow + H * xd + H;
+        for (int i = tid; i < HH; i += B2_NT) {
+            const int j = i >> 5, k = i & 31;
+            const float w = w1[i];
+            float sc1[L::NB1], sc2[L::NB2];
+            sc1[0] = 1.0f;
+            sc2[0] = 1.0f;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const float kap = sm[CF::SM_W0D + s * H + k];
+                sc2[1 + s] = kap;
+                if (s < NA2) {
+                    sc1[1 + s] = -2.0f * kap * kap;
+                    sc2[1 + NS + s] = -2.0f * kap * kap;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < L::NB1; ++v) {
+                uint32_t hi, lo;
+                tf32_split(w * sc1[v], hi, lo);
+                sm[L::OFF_B1 + (2 * v) * HH + bcore_index(j, k)] = __uint_as_float(hi);
+                sm[L::OFF_B1 + (2 * v + 1) * HH + bcore_index(j, k)] = __uint_as_float(lo);
+            }
+#pragma unroll
+            for (int v = 0; v < L::NB2; ++v) {
+                uint32_t hi, lo;
+                tf32_split(w * sc2[v], hi, lo);
+                sm[L::OFF_B2 + (2 * v) * HH + bcore_index(k, j)] = __uint_as_float(hi);
+                sm[L::OFF_B2 + (2 * v + 1) * HH + bcore_index(k, j)] = __uint_as_float(lo);
+            }
+        }
+    }
+    if (tid == 0) {
+        mbar_init(&bar_a1, B2_NPT);
+        mbar_init(&bar_a3, B2_NPT);
+        mbar_init(&bar_gtile, 1);
+        mbar_init(&bar_m1, 1);
+        mbar_init(&bar_m3, 1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_full[i], 64);        // the two warps of a quarter tile
+            mbar_init(&bar_free[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const int ntiles = (count + TP - 1) / TP;
+    if (warp < B2_NPW) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // frees 112 per thread = what the two point warpgroups take
+
+    float* red = sm + L::OFF_RING;            // end-of-item scratch (the ring is free once the last G MMA has completed)
+
+    if (warp < B2_NPW) {
+        // =============================================================================================
+        // point warps
+        // =============================================================================================
+        const int g = warp >> 2, q = warp & 3;
+        const int r = tid & 127;                    // point row of the tile = TMEM lane
+        const int j0 = 16 * g;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int slot = q & 1;
+        float* ring = sm + L::OFF_RING + slot * L::SLOT + (lane >> 2) * (int)(GK_LBO / 4) + (lane & 3) + 2 * g * (int)(GK_SBO / 4);
+        float wlacc[16], b1acc[16], l0acc[2] = {0.0f, 0.0f}, blacc = 0.0f;      // per-thread partial sums over the item
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { wlacc[u] = 0.0f; b1acc[u] = 0.0f; }
+        float gacc[48];                             // this thread's 48 columns of its G lane, summed over the tiles
+#pragma unroll
+        for (int u = 0; u < 48; ++u) gacc[u] = 0.0f;
+        auto gather_g = [&](uint32_t parity) {      // add the G block of a finished tile (the MMA warp has committed it)
+            mbar_wait_or_trap(&bar_gtile, parity);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) {
+                uint32_t v[8];
+                tmem_ld8(tbase + lane_base + COL_G + 48 * g + 8 * ch, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gacc[8 * ch + e] += __uint_as_float(v[e]);
+            }
+        };
+
+        int pf_pt = 0, pf_row = 0;
+        float pf_x[3] = {0.0f, 0.0f, 0.0f}, pf_g[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) pf_g[c] = 0.0f;
+        auto load_idx = [&](int t0n) {
+            if (t0n < count) {
+                const int cn = min(TP, count - t0n);
+                const int pi = first + t0n + (r < cn ? r : 0);
+                pf_pt = a.spair_point[pi];
+                pf_row = a.spair_row[pi];
+            }
+        };
+        auto load_val = [&](int t0n) {
+            if (t0n < count) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
+                const float* gr = a.grow + (int64_t)pf_row * C;
+#pragma unroll
+                for (int c = 0; c < C; ++c) pf_g[c] = gr[a.ext[c]];
+            }
+        };
+        load_idx(0);
+        load_val(0);
+
+        for (int t = 0; t < ntiles; ++t) {
+            const int t0 = t * TP;
+            const int cnt = min(TP, count - t0);
+            const uint32_t par = (uint32_t)(t & 1);
+
+            // ---- S0: coordinates, window jets, cotangent of the output-layer jets ----------------------
+            float z[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
+            float rb[C];
+            {
+                float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
+                fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
+                const bool valid = r < cnt;
+                float G[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) G[c] = valid ? pf_g[c] : 0.0f;
+                float ub0 = G[0] * w;
+#pragma unroll
+                for (int s = 0; s < NA2; ++s) {
+                    const float G1 = G[1 + 2 * s], G2 = G[2 + 2 * s];
+                    ub0 += G1 * w1[s] + G2 * w2[s];
+                    rb[1 + 2 * s] = un_sd * (G1 * w + 2.0f * G2 * w1[s]);
+                    rb[2 + 2 * s] = un_sd * (G2 * w);
+                }
+#pragma unroll
+                for (int s = 0; s < NA1; ++s) {
+                    const int c = 1 + 2 * NA2 + s;
+                    ub0 += G[c] * w1[NA2 + s];
+                    rb[c] = un_sd * (G[c] * w);
+                }
+                rb[0] = un_sd * ub0;
+                if (g == 0) blacc += rb[0];
+            }
+            load_idx(t0 + TP);
+
+            // ---- L: t, g of this thread's 16 units; A operands of MMA 1 (t, g kappa_s, t g) -> tensor memory ----
+            float tt[16], gg[16];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int jb = j0 + 8 * ch;
+                float av[CA1][8];
+#pragma unroll
+                for (int q4 = 0; q4 < 2; ++q4) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + jb + 4 * q4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + H + jb + 4 * q4);
+                    const float4 w2 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + 2 * H + jb + 4 * q4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(sm + CF::SM_B0 + jb + 4 * q4);
+                    float4 wd[NS > 0 ? NS : 1];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) wd[s] = *reinterpret_cast<const float4*>(sm + CF::SM_W0D + s * H + jb + 4 * q4);
+                    const float w0a[4] = {w0.x, w0.y, w0.z, w0.w}, w1a[4] = {w1.x, w1.y, w1.z, w1.w};
+                    const float w2a[4] = {w2.x, w2.y, w2.z, w2.w}, b0a[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const int e = 4 * q4 + e4;
+                        const float a0 = fmaf(w2a[e4], z[2], fmaf(w1a[e4], z[1], fmaf(w0a[e4], z[0], b0a[e4])));
+                        const float tv = fbp_tanh(a0);
+                        const float gv = 1.0f - tv * tv;
+                        tt[8 * ch + e] = tv;
+                        gg[8 * ch + e] = gv;
+                        av[0][e] = tv;
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+                            av[1 + s][e] = gv * (e4 == 0 ? wd[s].x : (e4 == 1 ? wd[s].y : (e4 == 2 ? wd[s].z : wd[s].w)));
+                        if (NA2 > 0) av[CA1 - 1][e] = tv * gv;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CA1; ++i) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        hi[e] = __float_as_uint(av[i][e]);
+                        lo[e] = __float_as_uint(tf32_lo(av[i][e]));
+                    }
+                    tmem_st8(tbase + lane_base + i * 32 + jb, hi);
+                    tmem_st8(tbase + lane_base + L::COL_A1LO + i * 32 + jb, lo);
+                }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bar_a1);                              // A of MMA 1 written; D3 of the previous tile read
+            load_val(t0 + TP);
+
+            // ---- E1: a2 -> h2, output-layer gradient partials, tanh transpose -> abar2 -> A operands of MMA 3 ---------
+            mbar_wait_or_trap(&bar_m1, par);                   // all of MMA 1: a2 is final and its A operands may be overwritten
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int jb = j0 + 8 * ch;
+                uint32_t v[C][8];
+#pragma unroll
+                for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + L::COL_D1 + c * 32 + jb, v[c]);
+                tmem_wait_ld();
+                float ab[8][C];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float h2[C], hb[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) h2[c] = __uint_as_float(v[c][e]);
+                    h2[0] += sm[CF::SM_B1 + jb + e];
+                    fast_tanh_jets<CF>(h2);
+                    const float wl = sm[CF::SM_WL + jb + e];
+                    float dsum = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        dsum = fmaf(rb[c], h2[c], dsum);
+                        hb[c] = wl * rb[c];
+                    }
+                    wlacc[8 * ch + e] += dsum;
+                    fast_tanh_jets_bwd<CF>(h2, hb, ab[e]);
+                    b1acc[8 * ch + e] += ab[e][0];
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        hi[e] = __float_as_uint(ab[e][c]);
+                        lo[e] = __float_as_uint(tf32_lo(ab[e][c]));
+                    }
+                    tmem_st8(tbase + lane_base + c * 32 + jb, hi);
+                    tmem_st8(tbase + lane_base + L::COL_A3LO + c * 32 + jb, lo);
+                }
+            }
+            if (t > 0 && !(dbg & 1)) gather_g((uint32_t)((t - 1) & 1));   // the previous tile's G, before this tile's G overwrites it
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bar_a3);
+
+            // hi/lo images of abar2 and (t, g, t g) of this thread's point and units -> ring slot of the quarter tile.
+            // abar2 is read back from the hi columns of MMA 3's A operands (they hold the unsplit values) instead of
+            // living in 80 registers across E2.
+            auto ring_store = [&]() {
+                const uint32_t use = 2u * (uint32_t)t + (uint32_t)(q >> 1);
+                if (use > 0) mbar_wait_or_trap(&bar_free[slot], (use - 1) & 1);
+                auto put = [&](int img, int e, float x) {
+                    ring[img * GK_IMG + (e >> 3) * (int)(GK_SBO / 4) + (e & 7) * 4] = x;
+                };
+                if (!(dbg & 4))
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t v[C][8];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + c * 32 + j0 + 8 * ch, v[c]);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int e = 8 * ch + e8;
+                        const float x0 = __uint_as_float(v[0][e8]);
+                        put(L::img_at(0), e, x0);
+                        put(L::img_at(1), e, tf32_lo(x0));
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            const float x1 = __uint_as_float(v[s < NA2 ? 1 + 2 * s : 1 + 2 * NA2 + (s - NA2)][e8]);
+                            put(L::img_ag(0, s), e, x1);
+                            put(L::img_ag(1, s), e, tf32_lo(x1));
+                            if (s < NA2) {
+                                const float x2 = __uint_as_float(v[2 + 2 * s][e8]);
+                                put(L::img_atg(0, s), e, x2);
+                                put(L::img_atg(1, s), e, tf32_lo(x2));
+                            }
+                        }
+                        const float tv = tt[e], gv = gg[e], tg = tv * gv;
+                        put(L::img_phi(0, 0), e, tv);
+                        put(L::img_phi(0, 1), e, tf32_lo(tv));
+                        if (NS > 0) {
+                            put(L::img_phi(1, 0), e, gv);
+                            put(L::img_phi(1, 1), e, tf32_lo(gv));
+                        }
+                        if (NA2 > 0) {
+                            put(L::img_phi(2, 0), e, tg);
+                            put(L::img_phi(2, 1), e, tf32_lo(tg));
+                        }
+                    }
+                }
+                fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
+                mbar_arrive(&bar_full[slot]);
+            };
+            if (q < 2 && !(dbg & 1)) ring_store();             // quarters 0, 1 own the slots first; 2, 3 after their E2
+
+            // ---- E2: abar0 = g D_t - 2 t g D_g + g (1 - 3 t^2) D_tg  -> first-layer gradient partials ------------------
+            mbar_wait_or_trap(&bar_m3, par);                   // all of MMA 3: its A operands may be rewritten by the next tile
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int kb = j0 + 8 * ch;
+                uint32_t vt[8], vg[8], vtg[8];
+                tmem_ld8(tbase + lane_base + L::COL_D3 + kb, vt);
+                if (NS > 0) tmem_ld8(tbase + lane_base + L::COL_D3 + 32 + kb, vg);
+                if (NA2 > 0) tmem_ld8(tbase + lane_base + L::COL_D3 + 64 + kb, vtg);
+                tmem_wait_ld();
+                float qv[32];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float tv = tt[8 * ch + e], gv = gg[8 * ch + e];
+                    float acc = __uint_as_float(vt[e]);
+                    if (NS > 0) acc = fmaf(-2.0f * tv, __uint_as_float(vg[e]), acc);
+                    if (NA2 > 0) acc = fmaf(fmaf(-3.0f * tv, tv, 1.0f), __uint_as_float(vtg[e]), acc);
+                    const float ab0 = gv * acc;
+                    qv[4 * e + 0] = ab0;
+                    qv[4 * e + 1] = ab0 * z[0];
+                    qv[4 * e + 2] = ab0 * z[1];
+                    qv[4 * e + 3] = ab0 * z[2];
+                }
+                l0acc[ch] += (dbg & 32) ? qv[0] + qv[9] + qv[18] + qv[27] : warp_transpose_reduce32(qv, lane);
+            }
+            if (q >= 2 && !(dbg & 1)) ring_store();
+        }
+        // ---- end of item: every partial to shared memory.  The last G MMA has completed (so has every ring store). ------
+        if (ntiles > 0 && !(dbg & 1)) gather_g((uint32_t)((ntiles - 1) & 1));     // also: every ring read has completed
+#pragma unroll
+        for (int u = 0; u < 48; ++u) red[L::RED_GD + (q * 32 + lane) * 96 + 48 * g + u] = gacc[u];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) red[L::RED_L0 + (warp * 2 + ch) * 32 + lane] = l0acc[ch];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            red[L::RED_WL + u * B2_NPT + tid] = wlacc[u];
+            red[L::RED_B1 + u * B2_NPT + tid] = b1acc[u];
+        }
+        const float bv = fbp_warp_sum(blacc);
+        if (lane == 0) red[L::RED_BL + warp] = bv;
+    } else if (warp == B2_NPW) {
+        // =============================================================================================
+        // MMA warp
+        // =============================================================================================
+        const uint32_t b1 = smem_u32(sm + L::OFF_B1), b2 = smem_u32(sm + L::OFF_B2);
+        auto b1d = [&](int v, int part) { return make_smem_desc(b1 + (uint32_t)((2 * v + part) * HH * 4), B_LBO, B_SBO); };
+        auto b2d = [&](int v, int part) { return make_smem_desc(b2 + (uint32_t)((2 * v + part) * HH * 4), B_LBO, B_SBO); };
+        const uint32_t ring0 = smem_u32(sm + L::OFF_RING);
+        constexpr uint32_t idesc_g = make_idesc_tf32(128, 32);
+        for (int t = 0; t < ntiles; ++t) {
+            const uint32_t par = (uint32_t)(t & 1);
+            // ---- MMA 1: a2[c] = A1[ia(c)] * B1[vb(c)]^T, unit half 0 first ------------------------------------
+            mbar_wait_or_trap(&bar_a1, par);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    int ia = 0, vb = 0;
+                    if (c > 0 && c <= 2 * NA2) {
+                        const int s = (c - 1) >> 1;
+                        if ((c - 1) & 1) { ia = CA1 - 1; vb = 1 + s; }      // second order: (t g) against W1 diag(-2 kappa_s^2)
+                        else ia = 1 + s;
+                    } else if (c > 0) ia = 1 + NA2 + (c - 1 - 2 * NA2);
+                    issue_gemm_acc<32>(tbase + L::COL_D1 + c * 32, tbase + ia * 32, tbase + L::COL_A1LO + ia * 32, b1d(vb, 0), b1d(vb, 1), true);
+                }
+                mma_commit(&bar_m1);
+            }
+            __syncwarp();
+            // ---- MMA 3: D_t, D_g, D_tg ---------------------------------------------------------------------------
+            mbar_wait_or_trap(&bar_a3, par);
+            tc_fence_after();
+            if (elect_one()) {
+                issue_gemm_acc<32>(tbase + L::COL_D3, tbase, tbase + L::COL_A3LO, b2d(0, 0), b2d(0, 1), true);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const int c1 = s < NA2 ? 1 + 2 * s : 1 + 2 * NA2 + (s - NA2);
+                    issue_gemm_acc<32>(tbase + L::COL_D3 + 32, tbase + c1 * 32, tbase + L::COL_A3LO + c1 * 32, b2d(1 + s, 0), b2d(1 + s, 1), s == 0);
+                }
+#pragma unroll
+                for (int s = 0; s < NA2; ++s) {
+                    const int c2 = 2 + 2 * s;
+                    issue_gemm_acc<32>(tbase + L::COL_D3 + 64, tbase + c2 * 32, tbase + L::COL_A3LO + c2 * 32, b2d(1 + NS + s, 0),
+                                       b2d(1 + NS + s, 1), s == 0);
+                }
+                mma_commit(&bar_m3);
+            }
+            __syncwarp();
+            // ---- G: weight-gradient products of the four quarter tiles, accumulated over the whole work item --------
+            if (!(dbg & 1))
+#pragma unroll 1
+            for (int qi = 0; qi < 4; ++qi) {
+                const int slot = qi & 1;
+                mbar_wait_or_trap(&bar_full[slot], (uint32_t)(qi >> 1));
+                if (elect_one()) {
+                    const uint32_t rbase = ring0 + (uint32_t)(slot * L::SLOT * 4);
+                    const bool fresh = (qi == 0);                 // every tile starts fresh accumulators
+                    auto block = [&](int a_img, int b_img, uint32_t dcol) {
+                        const uint64_t ad = make_smem_desc(rbase + (uint32_t)(a_img * GK_IMG * 4), GK_LBO, GK_SBO);
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            const uint64_t bd = make_smem_desc(rbase + (uint32_t)((b_img + part) * GK_IMG * 4), GK_LBO, GK_SBO);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t adv = (uint64_t)((ks * 2 * GK_LBO) >> 4);
+                                mma_tf32_ss(tbase + dcol, ad + adv, bd + adv, idesc_g, (fresh && part == 0 && ks == 0) ? 0u : 1u);
+                            }
+                        }
+                    };
+                    if (!(dbg & 8)) {
+                        if (NS > 0) block(L::img_ag(0, 0), L::img_phi(1, 0), COL_G);
+                        if (NA2 > 0) block(L::img_atg(0, 0), L::img_phi(2, 0), COL_G + 32);
+                        block(L::img_at(0), L::img_phi(0, 0), COL_G + 64);
+                    }
+                    mma_commit(&bar_free[slot]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) mma_commit(&bar_gtile);           // this tile's G is complete when this arrives
+            __syncwarp();
+        }
+
+    }
+
+    __syncthreads();
+
+    const float* gd = red + L::RED_GD;
+    // G_g[s][j][k], G_tg[s][j][k], G_t[j][k]: the hi and lo rows of the stacks added
+    auto Gg = [&](int s, int j, int k) { return gd[(32 * s + j) * 96 + k] + gd[(64 + 32 * s + j) * 96 + k]; };
+    auto Gtg = [&](int s, int j, int k) { return gd[(32 * s + j) * 96 + 32 + k] + gd[(64 + 32 * s + j) * 96 + 32 + k]; };
+    auto Gt = [&](int j, int k) { return gd[j * 96 + 64 + k] + gd[(32 + j) * 96 + 64 + k]; };
+    // derivative path of the first layer: kappa_bar_s[k] = sum_j W1[j][k] (G_g[s][j][k] - 4 kappa_s[k] G_tg[s][j][k])
+    for (int i = tid; i < NS * H; i += B2_NT) {
+        const int s = i >> 5, k = i & 31;
+        const float kap = sm[CF::SM_W0D + s * H + k];
+        float v = 0.0f;
+        for (int j = 0; j < H; ++j) {
+            float gsum = Gg(s, j, k);
+            if (s < NA2) gsum = fmaf(-4.0f * kap, Gtg(s, j, k), gsum);
+            v = fmaf(sm[CF::SM_WT1 + k * H + j], gsum, v);
+        }
+        red[L::RED_KB + i] = v;
+    }
+    __syncthreads();
+
+    float* gp = a.gpart + (int64_t)item * a.P;
+    // first layer, value path: (unit k, quantity t) sits in lane (k % 8) * 4 + t of chunk (k % 16) / 8 of the four point warps
+    // of unit half k / 16
+    auto l0 = [&](int k, int t) {
+        const int gg_ = k >> 4, ch = (k >> 3) & 1, ln = (k & 7) * 4 + t;
+        float v = 0.0f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) v += red[L::RED_L0 + ((gg_ * 4 + qq) * 2 + ch) * 32 + ln];
+        return v;
+    };
+    for (int i = tid; i < H * xd; i += B2_NT) {
+        const int j = i / xd, d = i - j * xd;
+        float v = l0(j, 1 + d);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (a.axis[s] == d) v = fmaf(sel3(d, isd[0], isd[1], isd[2]), red[L::RED_KB + s * H + j], v);
+        gp[i] = v;
+    }
+    for (int i = tid; i < H; i += B2_NT) gp[H * xd + i] = l0(i, 0);
+    int off = H * xd + H;
+    for (int i = tid; i < HH; i += B2_NT) {
+        const int j = i >> 5, k = i & 31;
+        float v = Gt(j, k);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float kap = sm[CF::SM_W0D + s * H + k];
+            v = fmaf(kap, Gg(s, j, k), v);
+            if (s < NA2) v = fmaf(-2.0f * kap * kap, Gtg(s, j, k), v);
+        }
+        gp[off + i] = v;
+    }
+    off += HH;
+    for (int i = tid; i < 2 * H; i += B2_NT) {      // hidden bias and output weights: sums over the 128 point threads of the unit's half
+        const int j = i & 31;
+        const float* src = red + (i < H ? L::RED_B1 : L::RED_WL) + (j & 15) * B2_NPT + (j >> 4) * 128;
+        float v = 0.0f;
+#pragma unroll 8
+        for (int p = 0; p < 128; ++p) v += src[p];
+        gp[off + i] = v;
+    }
+    off += 2 * H;
+    if (tid == 0) {
+        float v = 0.0f;
+        for (int w = 0; w < 4; ++w) v += red[L::RED_BL + w];    // warps 0-3 are unit half 0 (the only ones that count it)
+        gp[off] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);
+}
+
+}  // namespace fbptc

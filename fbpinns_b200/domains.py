@@ -53,13 +53,24 @@ class RectangularDomainND(Domain):
         d = all_params["static"]["domain"]
         xmin, xmax, xd = _as_np(d["xmin"]), _as_np(d["xmax"]), d["xd"]
         assert len(batch_shapes) == 2 * xd
+        # one independent key per face.  jax-style keys follow the reference's chain `key, subkey = split(key)` per face
+        # (fbpinns/domains.py:95); an int seed is expanded into per-face generators; a numpy Generator advances by itself
+        keys = []
+        if jax_prng.is_key(key):
+            for _ in range(2 * xd):
+                key, subkey = jax_prng.split(key)
+                keys.append(subkey)
+        elif isinstance(key, np.random.Generator) or key is None:
+            keys = [key] * (2 * xd)                 # None only occurs with the grid / quasi-random samplers
+        else:
+            keys = list(np.random.default_rng(key).spawn(2 * xd))
         out = []
         for i in range(xd):
             ic = [j for j in range(xd) if j != i]
             for j, v in enumerate([xmin[i], xmax[i]]):
                 bs = batch_shapes[2 * i + j]
                 if ic:
-                    xb_ = RectangularDomainND._rectangle_samplerND(key, sampler, xmin[ic], xmax[ic], bs)
+                    xb_ = RectangularDomainND._rectangle_samplerND(keys[2 * i + j], sampler, xmin[ic], xmax[ic], bs)
                     xb = torch.full((int(np.prod(bs)), xd), float(v), dtype=torch.float32)
                     xb[:, ic] = xb_
                 else:

@@ -214,7 +214,9 @@ def kernel_layers(network, all_params, device=None):
     act = getattr(network, "ACTIVATION", None)
     if act is None:
         raise NotImplementedError(f"{network} is not implemented by the B200 kernels")
-    to = (lambda t: t.to(device, torch.float32)) if device is not None else (lambda t: t.float())
+    # leaves may be torch tensors or numpy arrays (a checkpoint read by util.checkpoint.load_model holds numpy leaves)
+    as_t = lambda t: t if torch.is_tensor(t) else torch.as_tensor(np.asarray(t))
+    to = (lambda t: as_t(t).to(device, torch.float32)) if device is not None else (lambda t: as_t(t).float())
     layers = [tuple(to(t) for t in leaf) for leaf in all_params["trainable"]["network"]["subdomain"]["layers"]]
     if act == "fourier_tanh":
         omega = to(all_params["static"]["network"]["subdomain"]["omega"])           # (m, n_features, xd)

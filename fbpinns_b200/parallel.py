@@ -11,10 +11,15 @@ blocks of the global subdomain index (= slabs of grid rows along dimension 0, fb
     denominators D are exchanged once per active-set change;
   * the scalar loss and the gradients of the problem's own trainables are all-reduced.
 
-`loss_fn` must be a sum of per-constraint means (true for every reference problem): rank r scales the cotangents of
-constraint ic by n_owned(r, ic) / n(ic).  Gradients of the network parameters are then exact; gradients of the
-problem's own trainables and the reported loss use the weights of the first constraint (exact for single-constraint
-problems and whenever those quantities depend on one constraint only).
+Two ways to evaluate the loss (fbpinns/trainers.py:249-267 on the whole point set) on sharded points:
+  * "weighted" (single-constraint problems without trainables of their own, e.g. cfg 3-5): every rank evaluates
+    `loss_fn` on the points it owns; `loss_fn` must be a mean over points, so the global loss is sum_r (n_owned_r / n) L_r
+    and rank r scales its cotangents by n_owned_r / n.  No extra exchange.
+  * "replicated" (several constraints and / or problem trainables, e.g. cfg 1-2): the owners' ujs rows are summed into
+    the full (n_ic, V) array on every rank (one all-reduce of disjoint rows per constraint: exact), every rank evaluates
+    the SAME `loss_fn` on the full arrays and takes the rows it owns from the cotangent.  The loss, the gradients of the
+    problem's trainables and hence their Adam updates are then bit-identical on all ranks — no weights, no assumption
+    on the form of `loss_fn`, no empty-constraint special case.
 """
 
 import ctypes as C
@@ -267,10 +272,32 @@ def sharded_sum(sev, params, grads, tape_hook, weight):
     return _ShardedSum.apply(tape_hook, sev, params, grads, weight)
 
 
+class _ReplicateRows(torch.autograd.Function):
+    """(n_owned, V) rows of the owners -> the full (n, V) array on every rank (sum of disjoint rows: exact).  Every rank
+    then computes the same scalar from it, so the cotangent of the full array is the same everywhere and the reverse pass
+    is a row selection without communication."""
+
+    @staticmethod
+    def forward(ctx, rows, owned_idx, n, group):
+        ctx.owned_idx = owned_idx
+        full = torch.zeros((n, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        full.index_copy_(0, owned_idx, rows)
+        dist.all_reduce(full, group=group)
+        return full
+
+    @staticmethod
+    def backward(ctx, gfull):
+        return gfull.index_select(0, ctx.owned_idx), None, None, None
+
+
+def replicate_rows(rows, owned_idx, n, group=None):
+    return _ReplicateRows.apply(rows, owned_idx, n, group)
+
+
 # --------------------------------------------------------------------------------------------------- update inputs / step
 
 def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, constraints_global, constraint_offsets,
-                              jets, layer_sizes, kernel="auto", activation="tanh"):
+                              jets, layer_sizes, kernel="auto", activation="tanh", replicated=False):
     """Sharded counterpart of trainers.get_update_inputs: the global active-set algebra is identical on every rank
     (every rank holds the full point set and the full static decomposition — both small), then takes are built for
     this rank's block of subdomains over the points inside them."""
@@ -304,6 +331,7 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
     out.global_active_ims, out.global_all_ims = active_ims, all_ims
     out.pos_of_model, out.training_ips, out.d, out.x_batch = pos_loc, training_ips, d_stat, x_batch
     out.constraints, out.takess, out.evaluators, out.weights, out.halos = [], [], [], [], []
+    out.replicated, out.owned_global, out.n_constraint = bool(replicated), [], []
     sorted_all = np.sort(all_ims)
     for ic in range(len(constraints_global)):
         a, b = int(bounds[ic]), int(bounds[ic + 1])
@@ -327,12 +355,15 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
         ev = ConstraintEvaluator(plan, takes, x_loc, dd)
         sev = ShardedEvaluator(ev, halo, shard)
         owned_global = torch.as_tensor(halo["local_ips"][halo["owned_local"]].astype(np.int32), dtype=torch.int32, device=dev)
-        out.constraints.append([gather_rows(c_, owned_global) for c_ in con])      # the loss sees owned points only
+        # the loss sees the owned points only ("weighted") or every rank sees all points of the constraint ("replicated")
+        out.constraints.append(con if replicated else [gather_rows(c_, owned_global) for c_ in con])
+        out.owned_global.append(owned_global.long())
+        out.n_constraint.append(int(x_ic.shape[0]))
         out.takess.append(takes)
         out.evaluators.append(sev)
         out.halos.append(halo)
         n_ic = x_ic.shape[0]
-        out.weights.append(float(len(owned_global)) / float(max(n_ic, 1)))
+        out.weights.append(1.0 if replicated else float(len(owned_global)) / float(max(n_ic, 1)))
     return out
 
 
@@ -348,8 +379,10 @@ def make_sharded_update(base_cls):
         def forward_loss(self):
             self._refresh_problem_views()
             cons = []
-            for sev, con, w, aff in zip(self.inp.evaluators, self.inp.constraints, self.inp.weights, self.affine):
+            for ic, (sev, con, w, aff) in enumerate(zip(self.inp.evaluators, self.inp.constraints, self.inp.weights, self.affine)):
                 ujets = sharded_sum(sev, self.params, self.grads, self.hook, w)
+                if self.inp.replicated:
+                    ujets = replicate_rows(ujets, self.inp.owned_global[ic], self.inp.n_constraint[ic], self.shard.group)
                 jet = sev.ev.plan.jet
                 if aff is not None:
                     ujs = jet.ujs_plain(ujets)        # the kernels already returned the constrained jets
@@ -361,6 +394,9 @@ def make_sharded_update(base_cls):
             return self.problem.loss_fn(self.all_params, cons)
 
         def _eager(self):
+            if self.inp.replicated:
+                # every rank holds the global loss and identical problem-parameter gradients: nothing to reduce
+                return base_cls._eager(self)
             self.grads.zero_()
             self.hook.grad = None
             loss = self.forward_loss()

@@ -339,9 +339,12 @@ class FBPINNTrainer(_Trainer):
                                      c.use_cuda_graph)
         else:
             from . import parallel
+            # several constraints or trainables of the problem itself: evaluate loss_fn on the full ujs on every rank
+            replicated = len(self.constraints_global) > 1 or self.prob_flat is not None
             self.inputs = parallel.get_update_inputs_sharded(shard, active, self.all_params, self.dd, self.x_batch_global,
                                                              self.constraints_global, self.constraint_offsets, self.jets,
-                                                             self.layer_sizes, kernel=c.kernel, activation=self.activation)
+                                                             self.layer_sizes, kernel=c.kernel, activation=self.activation,
+                                                             replicated=replicated)
             self.update = parallel.make_sharded_update(UpdateStep)(shard, self.inputs, self.params, self.adam,
                                                                    self.all_params, self.prob_flat, c.problem,
                                                                    c.use_cuda_graph)
@@ -473,8 +476,10 @@ class FBPINNTrainer(_Trainer):
                 u_test = self.evaluate(x_batch_test)
                 if u_exact is not None:
                     l1 = torch.mean(torch.abs(u_exact - u_test)).item()
-                    l1n = l1 / u_exact.std().item()
-                    u_test_losses.append([i, time.time() - start0, l1, l1n])
+                    l1n = l1 / u_exact.std(unbiased=False).item()          # jnp.std: population standard deviation
+                    # row layout of the reference (fbpinns/trainers.py:757): [i, pstep, fstep, time, l1, l1n]; the
+                    # per-step FLOP counters pstep / fstep are not tracked here
+                    u_test_losses.append([i, 0, 0, time.time() - start0, l1, l1n])
                     logger.info(f"[i: {i}/{c.n_steps}] test l1: {l1:.5f} (normalised {l1n:.5f})")
                 report_time += time.time() - start2
         return u_test_losses, start1, report_time
@@ -483,14 +488,16 @@ class FBPINNTrainer(_Trainer):
         """Value-only FBPINN solution with ALL subdomains (FBPINN_model_jit / analysis.FBPINN_solution twin,
         fbpinns/trainers.py:314-320, 727-737): returns constrained u (n, ud)."""
         dd, plan = self.dd, self.value_plan
-        key = (x_batch.data_ptr(), x_batch.shape[0])
-        if self._test_eval is None or self._test_eval[0] != key:
+        # the takes are cached only for the very tensor object they were built for, unmodified since (identity + version
+        # counter; the cache holds a reference, so the address cannot be reused) — e.g. the trainer's own x_batch_test
+        cached = self._test_eval
+        if cached is None or cached[0] is not x_batch or cached[1] != x_batch._version:
             x = x_batch.to(dd.device, torch.float32).contiguous()
             _, mc = dd.inside_count(x)
             _, a_ims, f_ims, all_ims, pos = active_set_algebra(np.ones(dd.m, dtype=int), mc.cpu().numpy())
             takes = DeviceTakes(dd, x, pos, all_ims, len(a_ims), tile_points=plan.tile_points)
-            self._test_eval = (key, ConstraintEvaluator(plan, takes, x, dd, activation_cache=False), x)
-        _, ev, x = self._test_eval
+            self._test_eval = (x_batch, x_batch._version, ConstraintEvaluator(plan, takes, x, dd, activation_cache=False), x)
+        _, _, ev, x = self._test_eval
         with torch.no_grad():
             u = ev.forward(self.params)
             return self.c.problem.constraining_fn(self.all_params, x, u)

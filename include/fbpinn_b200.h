@@ -239,9 +239,10 @@ int fbp_ffma2_peak(int32_t iters, float* tflops, void* stream);
  * tcgen05 path the mode-3 kernels use (A written row-wise into tensor memory, B through a shared-memory descriptor,
  * 3xTF32).  `variant` = 0 for the shipped conventions; bits 0-2 probe alternatives (see fbp_tc.cu). */
 int fbp_tc_selftest(const float* d_a, const float* d_w, float* d_out, int32_t variant, void* stream);
-/* The same for the MN-major shared-memory operand form (both operands from shared memory, contraction over rows):
- * d_out[128][64] = sum_p d_a[p][0..128) (x) d_b[p][0..64), one TF32 pass on TF32-rounded inputs. */
-int fbp_tc_selftest_mn(const float* d_a, const float* d_b, float* d_out, int32_t variant, void* stream);
+/* Self-test of the operand form of the tensor-core weight gradient: both operands from shared memory, K-major with a
+ * padded K step, contraction over the 128 points of a tile accumulated quarter by quarter:
+ * d_out[128][32] = sum_p d_a[p][0..128) (x) d_b[p][0..32), one TF32 pass on TF32-rounded inputs. */
+int fbp_tc_selftest_g(const float* d_a, const float* d_b, float* d_out, int32_t variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -130,7 +130,8 @@ def test_trainer_end_to_end_and_active_set_changes():
     c = configs.cfg1_harmonic_oscillator(n_steps=300, summary_freq=100, test_freq=100)
     run = FBPINNTrainer(c)
     run.train()
-    l1 = [r[2] for r in run.u_test_losses]
+    l1 = [r[4] for r in run.u_test_losses]
+    assert all(len(r) == 6 for r in run.u_test_losses)        # the reference's row layout [i, pstep, fstep, t, l1, l1n]
     assert len(l1) >= 3 and np.isfinite(l1).all()
     u = run.evaluate(torch.linspace(0, 1, 50, device="cuda:0").reshape(-1, 1))
     assert u.shape == (50, 1) and torch.isfinite(u).all()

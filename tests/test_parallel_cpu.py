@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 from oracle import ref_takes
 from fbpinns_b200 import configs
-from fbpinns_b200.parallel import Shard, build_halo_lists, HaloExchange
+from fbpinns_b200.parallel import Shard, build_halo_lists, HaloExchange, replicate_rows
 
 
 def _geometry(world):
@@ -71,7 +71,18 @@ def _worker(rank, world, port, q):
         back = torch.tensor(np.where(own, g, 0.0)[:, None].repeat(3, 1), dtype=torch.float64)
         ex.backward_return(back)
         ok_bwd = np.allclose(back.numpy()[:, 0], g)
-        q.put((rank, bool(ok_fwd), bool(ok_bwd), int(own.sum()), int(len(lips))))
+        # "replicated" loss evaluation: owners' rows -> the full array on every rank; a scalar of the full array
+        # differentiates back to exactly the owned rows (multi-constraint problems / problem trainables)
+        n = mask.shape[0]
+        owned_global = torch.as_tensor(lips[own], dtype=torch.long)
+        vals = torch.tensor(np.stack([np.cos(lips[own] * 0.11), lips[own] * 1.0], 1), dtype=torch.float64, requires_grad=True)
+        full = replicate_rows(vals, owned_global, n)
+        wts = torch.arange(1, n + 1, dtype=torch.float64)[:, None] * torch.tensor([[1.0, -2.0]], dtype=torch.float64)
+        (full * wts).sum().backward()
+        ok_rep = (np.allclose(full.detach().numpy()[:, 0], np.cos(np.arange(n) * 0.11)) and
+                  np.allclose(full.detach().numpy()[:, 1], np.arange(n) * 1.0) and
+                  np.allclose(vals.grad.numpy(), wts.numpy()[lips[own]]))
+        q.put((rank, bool(ok_fwd), bool(ok_bwd and ok_rep), int(own.sum()), int(len(lips))))
     finally:
         dist.destroy_process_group()
 

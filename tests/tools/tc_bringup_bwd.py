@@ -36,6 +36,7 @@ def run(tag, kw, reps, breakdown):
     tr.set_active(np.ones(tr.all_params["static"]["decomposition"]["m"], dtype=int))
     ev = tr.inputs.evaluators[0]
     ev = getattr(ev, "ev", ev)
+    ev.set_affine(None)          # compare the subdomain kernels only (the tensor evaluator below carries no affine operator either)
     plan_t = Plan(ev.plan.layer_sizes, ev.plan.jet, kernel="tensor-full")
     assert plan_t.kernel == "tensor-full", "no tensor instance for this plan"
     ev_t = ConstraintEvaluator(plan_t, ev.takes, ev.x, tr.dd)
@@ -80,7 +81,7 @@ def run(tag, kw, reps, breakdown):
     res[f"{tag}_tiled_bwd_ms"] = timed(ev, g_ref)
     res[f"{tag}_tensor_bwd_ms"] = timed(ev_t, g_t)
     if breakdown:
-        for dbg in (16, 2, 18, 32, 50):
+        for dbg in ((1, 4, 8, 32, 33) if os.environ.get("FBP_TC_BWD", "1") == "2" else (16, 2, 18, 32, 50)):
             os.environ["FBP_TC_DEBUG"] = str(dbg)
             res[f"{tag}_tensor_bwd_dbg{dbg}_ms"] = timed(ev_t, g_t)
         os.environ["FBP_TC_DEBUG"] = "0"

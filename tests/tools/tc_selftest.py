@@ -27,7 +27,7 @@ def run_variant(variant, mn=False):
     if rt is None:
         raise SystemExit("libcudart not found")
     lib = C.CDLL(os.path.join(ROOT, "fbpinns_b200", "csrc", "libfbpinn_b200.so"))
-    fn = lib.fbp_tc_selftest_mn if mn else lib.fbp_tc_selftest
+    fn = lib.fbp_tc_selftest_g if mn else lib.fbp_tc_selftest
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.fbp_last_error.restype = C.c_char_p
@@ -40,11 +40,11 @@ def run_variant(variant, mn=False):
             raise SystemExit(f"{what}: cuda error {rc} {rt.cudaGetErrorString(rc).decode()}")
 
     rng = np.random.default_rng(0)
-    if mn:      # out[m][n] = sum_p a[p][m] w[p][n], inputs pre-rounded to TF32 so that a single pass is exact
+    if mn:      # --mn: the ss form of the weight gradient (fbp_tc_selftest_g): out[m][n] = sum_p a[p][m] w[p][n], inputs pre-rounded to TF32 so that a single pass is exact
         tf32 = lambda v: ((v.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
         a = tf32(rng.standard_normal((128, 128)).astype(np.float32))
-        w = tf32(rng.uniform(-1, 1, (128, 64)).astype(np.float32))
-        out = np.full((128, 64), np.nan, dtype=np.float32)
+        w = tf32(rng.uniform(-1, 1, (128, 32)).astype(np.float32))
+        out = np.full((128, 32), np.nan, dtype=np.float32)
     else:
         a = rng.standard_normal((128, 32)).astype(np.float32)
         w = rng.uniform(-1, 1, (32, 32)).astype(np.float32)
@@ -64,8 +64,13 @@ def run_variant(variant, mn=False):
     else:
         ref = a.astype(np.float64) @ w.astype(np.float64).T
         scale = (np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T).max()
+    if mn and (variant & 4):         # M = 64: find which tensor-memory lane holds each accumulator row
+        lanes = [int(np.argmin(np.abs(out - ref[r]).max(axis=1))) for r in range(64)]
+        errs = [float(np.abs(out[l] - ref[r]).max() / scale) for r, l in enumerate(lanes)]
+        print(json.dumps({"form": "k-major ss M=64", "variant": variant, "row_to_lane": lanes, "max_err_rel": max(errs)}))
+        return
     err = np.abs(out - ref)
-    res = {"form": "mn-major ss" if mn else "k-major ts", "variant": variant, "max_err_rel": float(np.nanmax(err) / scale), "nan": int(np.isnan(out).sum()),
+    res = {"form": "k-major ss (weight-gradient operands)" if mn else "k-major ts", "variant": variant, "max_err_rel": float(np.nanmax(err) / scale), "nan": int(np.isnan(out).sum()),
            "bad_rows": int((err.max(axis=1) / scale > 1e-5).sum()), "bad_cols": int((err.max(axis=0) / scale > 1e-5).sum()),
            "out00": float(out[0, 0]), "ref00": float(ref[0, 0])}
     print(json.dumps(res))
@@ -76,7 +81,7 @@ if __name__ == "__main__":
         run_variant(int(sys.argv[2]), mn="--mn" in sys.argv)
         sys.exit(0)
     mn = "--mn" in sys.argv
-    variants = [int(v) for v in sys.argv[1:] if v != "--mn"] or ([0, 1] if mn else [0, 4, 1, 2])
+    variants = [int(v) for v in sys.argv[1:] if v != "--mn"] or ([0, 2, 4] if mn else [0, 4, 1, 2])
     lines = []
     for v in variants:
         try:

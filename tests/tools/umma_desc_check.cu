@@ -37,28 +37,20 @@ int main() {
         printf("instr desc: cute %08x %08x ours %08x %08x\n", (unsigned)i16.desc_, (unsigned)i32.desc_, fbptc::make_idesc_tf32(128, 16), fbptc::make_idesc_tf32(128, 32));
         ++bad;
     }
-    // MN-major SWIZZLE_NONE operands (planned tensor-core weight gradient): layout and the strides make_umma_desc<MN> uses
-    {
-        auto la = tile_to_shape(UMMA::Layout_MN_INTER_Atom<T>{}, Shape<_128, _128>{});
-        auto lb = tile_to_shape(UMMA::Layout_MN_INTER_Atom<T>{}, Shape<_64, _128>{});
-        int bad_mn = 0;
-        for (int k = 0; k < 128; ++k) {
-            for (int mn = 0; mn < 128; ++mn) if ((int)la(mn, k) != fbptc::mncore_index(mn, k, 128)) ++bad_mn;
-            for (int mn = 0; mn < 64; ++mn) if ((int)lb(mn, k) != fbptc::mncore_index(mn, k, 64)) ++bad_mn;
+    // operand images of the tensor-core weight gradient: the same canonical K-major form with a padded K step; with the
+    // unpadded step it must coincide with the layout above, and the padded strides are what the descriptor carries
+    for (int n = 0; n < 32; ++n)
+        for (int k = 0; k < 32; ++k) {
+            if (fbptc::gk_index(n, k, 128) != fbptc::bcore_index(n, k)) ++bad;
+            if (fbptc::gk_index(n, k) != (n >> 3) * (int)(fbptc::GK_SBO / 4) + (k >> 2) * (int)(fbptc::GK_LBO / 4) + (n & 7) * 4 + (k & 3)) ++bad;
         }
-        if (bad_mn) { printf("MN-major layout: %d elements differ\n", bad_mn); ++bad; }
-        auto ua = logical_divide(recast_layout<T, uint128_t>(la.layout_b()), Tile<Layout<_1>, Layout<_8>>{});
-        auto ub = logical_divide(recast_layout<T, uint128_t>(lb.layout_b()), Tile<Layout<_1>, Layout<_8>>{});
-        // SWIZZLE_NONE, MN-major: stride_byte_offset = stride<0,1> (MN groups), leading_byte_offset = stride<1,1> (K groups)
-        const uint32_t a_sbo = (uint32_t)stride<0, 1>(ua) * 16, a_lbo = (uint32_t)stride<1, 1>(ua) * 16;
-        const uint32_t b_sbo = (uint32_t)stride<0, 1>(ub) * 16, b_lbo = (uint32_t)stride<1, 1>(ub) * 16;
-        if (a_sbo != fbptc::MN_SBO || a_lbo != fbptc::mn_lbo(128) || b_sbo != fbptc::MN_SBO || b_lbo != fbptc::mn_lbo(64)) {
-            printf("MN strides: cute A (SBO %u, LBO %u) B (%u, %u), ours A (%u, %u) B (%u, %u)\n", a_sbo, a_lbo, b_sbo, b_lbo,
-                   fbptc::MN_SBO, fbptc::mn_lbo(128), fbptc::MN_SBO, fbptc::mn_lbo(64));
-            ++bad;
+    static_assert(fbptc::GK_LBO % 16 == 0 && fbptc::GK_SBO % 16 == 0, "descriptor strides are in units of 16 bytes");
+    {   // 32 lanes storing one image row (32 consecutive points) must hit 32 different banks
+        for (int row = 0; row < 32; ++row) {
+            unsigned seen = 0;
+            for (int k = 0; k < 32; ++k) seen |= 1u << (fbptc::gk_index(row, k) & 31);
+            if (seen != 0xffffffffu) ++bad;
         }
-        auto imn = UMMA::make_instr_desc<T, T, float, 128, 64, UMMA::Major::MN, UMMA::Major::MN>();
-        if (imn.desc_ != fbptc::make_idesc_tf32(128, 64, 1, 1)) { printf("MN instr desc: cute %08x ours %08x\n", (unsigned)imn.desc_, fbptc::make_idesc_tf32(128, 64, 1, 1)); ++bad; }
     }
     printf(bad ? "MISMATCH\n" : "OK\n");
     return bad ? 1 : 0;
