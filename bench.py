@@ -294,11 +294,18 @@ def run_ours(args):
     s_local, s_active = takes.s, takes.s_active
     bwd_tf = 2.0 * f_fwd * s_active / (bwd_ms * 1e-3) / 1e12
     fwd_tf = f_fwd * s_local / (fwd_ms * 1e-3) / 1e12
+    # names of the kernels fbp_forward / fbp_backward launch for this plan (the dominant one is the reverse kernel)
+    bwd_kernel = {"generic": "generic_backward_kernel", "tiled": "fast_backward_kernel",
+                  "tensor": "tc_backward_kernel2" if os.environ.get("FBP_TC_BWD", "2") == "2" else "tc_backward_kernel"}[ev.plan.reverse_family]
+    fwd_kernel = {"generic": "generic_forward_kernel", "tiled": "fast_forward_kernel",
+                  "tensor": "tc_forward_kernel2" if os.environ.get("FBP_TC_FWD", "2") == "2" else "tc_forward_kernel"}[ev.plan.forward_family]
+    # DRAM bytes per launch of THAT kernel from the committed ncu capture (profiles/traffic.json, written by
+    # profiles/summarise.py from `ncu --set full`: dram__bytes_read.sum + dram__bytes_write.sum); null if never captured
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.config == "cfg5" and not args.small:
         try:
-            traffic = json.load(open(tpath)).get("fast_backward_kernel")
+            traffic = json.load(open(tpath)).get(bwd_kernel)
         except Exception:
             traffic = None
     peaks = {}
@@ -315,6 +322,7 @@ def run_ours(args):
 
     # ---- active-set change path: full rebuild of the update inputs on the device (inside tests, takes,
     #      work list, window sums, affine jets) — what costs the reference an O(n m) index pass + an XLA recompile
+    graph_replayed = tr.update.graph is not None          # read before the rebuild below discards the captured graph
     rebuild_ms = None
     if world == 1 and not args.skip_rebuild:
         torch.cuda.synchronize()
@@ -342,8 +350,9 @@ def run_ours(args):
                                                   f"{kw['n_pts'][0]}x{kw['n_pts'][1]} grid (not the headline workload)",
                        "layers": list(layer_sizes), "subdomains": m, "points": n_points_global,
                        "pairs_this_rank": s_local, "parallelism": f"subdomain-slabs x{world}" if world > 1 else "single GPU",
-                       "cuda_graph": tr.update.graph is not None, "kernel_family": ("tensor forward + tensor reverse (tcgen05 3xTF32, weight gradient on FFMA2)" if ev.plan.kernel == "tensor-full" else
-                                         {"generic": "generic", "tiled": "tiled", "tensor": "tensor forward (tcgen05 3xTF32) + tiled reverse"}[ev.plan.forward_family]),
+                       "cuda_graph": graph_replayed,
+                       "kernel_family": f"forward {ev.plan.forward_family} ({fwd_kernel}), reverse {ev.plan.reverse_family} ({bwd_kernel})"
+                                        + ("; tensor = tcgen05 3xTF32, FP32-equivalent accuracy" if "tensor" in (ev.plan.forward_family, ev.plan.reverse_family) else ""),
                        "l2": "per-step working set (pair jets 175 MB + indices 105 MB) exceeds the 126 MB L2; "
                              "per-kernel timings flush L2 with a 256 MB write between launches"},
             "ujs_point_evals_per_sec": int(tr.x_batch_global.shape[0]) * steps_per_s,
@@ -353,7 +362,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_steps_per_s, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": gpu_launches,
-            "roofline": {"bound": "fp32_fma", "kernel": "tc_backward_kernel" if ev.plan.kernel == "tensor-full" else "fast_backward_kernel",
+            "roofline": {"bound": "fp32_fma", "kernel": bwd_kernel,
                          "achieved": bwd_tf, "peak": fma_peak,
                          "unit": "TFLOP/s", "frac": bwd_tf / fma_peak if fma_peak else None,
                          "peak_source": "max of the FFMA and FFMA2 (fma.rn.f32x2) micro-benchmarks on this GPU (fbp_fma_peak / "
@@ -361,7 +370,7 @@ def run_ours(args):
                          "peak_ffma": fma_scalar, "peak_ffma2": fma_packed, "peak_nominal": nominal,
                          "launch_ms": bwd_ms, "launch_ms_best": bwd_best, "flops_per_launch": 2.0 * f_fwd * s_active,
                          "traffic": traffic,
-                         "forward": {"kernel": "tc_forward_kernel" if ev.plan.forward_family == "tensor" else "fast_forward_kernel",
+                         "forward": {"kernel": fwd_kernel,
                                      "achieved": fwd_tf, "frac": fwd_tf / fma_peak if fma_peak else None,
                                      "launch_ms": fwd_ms, "flops_per_launch": float(f_fwd * s_local),
                                      "note": ("hidden GEMM on the tcgen05 tensor cores in 3xTF32 (FP32-equivalent accuracy); the "

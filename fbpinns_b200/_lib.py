@@ -58,6 +58,7 @@ SIGNATURES = {
     "fbp_plan_set_kernel": (C.c_int, [_P, _I32]),
     "fbp_plan_has_tensor": (_I32, [_P]),
     "fbp_plan_forward_family": (_I32, [_P]),
+    "fbp_plan_reverse_family": (_I32, [_P]),
     "fbp_plan_scratch_per_pair": (_I64, [_P]),
     "fbp_plan_cache_per_pair": (_I64, [_P]),
     "fbp_pack_params": (C.c_int, [_P, _I64, C.POINTER(_P), C.POINTER(_P), _P, _P]),

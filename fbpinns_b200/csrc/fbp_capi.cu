@@ -134,6 +134,11 @@ int32_t fbp_plan_forward_family(const fbp_plan* plan) {
     return !plan->use_fast() ? 0 : (plan->use_tc() ? 2 : 1);
 }
 
+int32_t fbp_plan_reverse_family(const fbp_plan* plan) {
+    if (!plan) return -1;
+    return !plan->use_fast() ? 0 : (plan->use_tc_bwd() ? 2 : 1);
+}
+
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode) {
     FBP_REQUIRE(plan, "fbp_plan_set_kernel: null plan");
     FBP_REQUIRE(mode >= 0 && mode <= 4, "fbp_plan_set_kernel: mode must be 0 .. 4");

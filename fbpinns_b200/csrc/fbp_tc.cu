@@ -253,20 +253,25 @@ static int tc_backward_one(FastArgs a, int grid, cudaStream_t st) {
     return 0;
 }
 
-// second generation: weight gradient on the tensor core (fbp_tc_bwd2.cuh)
-template <class CF>
-static int tc_backward_two(FastArgs a, int grid, cudaStream_t st) {
-    constexpr size_t bytes = sizeof(float) * Bwd2Cfg<CF>::FLOATS;
+// second generation: weight gradient on the tensor core (fbp_tc_bwd2.cuh); FBP_TC_NG = 2 | 4 unit groups (8 | 16 point warps)
+template <class CF, int NG>
+static int tc_backward_two_ng(FastArgs a, int grid, cudaStream_t st) {
+    constexpr size_t bytes = sizeof(float) * Bwd2Cfg<CF, NG>::FLOATS;
     static_assert(bytes <= 226 * 1024, "reverse kernel 2: shared memory budget");
-    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel2<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel2<CF, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     a.dbg = env_int("FBP_TC_DEBUG", 0);
-    tc_backward_kernel2<CF><<<grid, B2_NT, bytes, st>>>(a);
+    tc_backward_kernel2<CF, NG><<<grid, B2Dim<NG>::NT, bytes, st>>>(a);
     FBP_LAUNCH_CHECK();
     return 0;
 }
+template <class CF>
+static int tc_backward_two(const FastArgs& a, int grid, cudaStream_t st) {
+    if (env_int("FBP_TC_NG", 4) == 2) return tc_backward_two_ng<CF, 2>(a, grid, st);
+    return tc_backward_two_ng<CF, 4>(a, grid, st);
+}
 
 int fbp_tc_backward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaStream_t st) {
-    if (env_int("FBP_TC_BWD", 1) == 2) {
+    if (env_int("FBP_TC_BWD", 2) == 2) {       // default since it was timed: 4.43 vs 5.21 ms (profiles/r2c_tc_bwd2.md)
         switch (f.na2 * 4 + f.na1) {
             case 0: return tc_backward_two<FastCfg<32, 2, 0, 0>>(a, grid, st);
             case 1: return tc_backward_two<FastCfg<32, 2, 0, 1>>(a, grid, st);

@@ -33,13 +33,24 @@
 
 namespace fbptc {
 
-constexpr int B2_NPW = 8;                 // point warps
-constexpr int B2_NPT = B2_NPW * 32;       // 256 point threads
-constexpr int B2_NT = B2_NPT + 128;       // + the MMA warpgroup (warp 8 issues, warps 9-11 only help at the end of the item)
+// NG = unit groups per point row: thread (g, p) owns point row p and the hidden units [UPT g, UPT (g + 1)).  NG = 2: 8 point
+// warps of 16 units per thread (224 registers); NG = 4: 16 point warps of 8 units (112 registers, 4 warps per scheduler
+// to hide the MMA / TMEM / MUFU latencies the 8-warp version is bound by: 29 % issue utilisation, profiles/r2bwd2_kernels.md).
+template <int NG>
+struct B2Dim {
+    static_assert(NG == 2 || NG == 4, "2 or 4 unit groups");
+    static constexpr int NPW = 4 * NG;              // point warps
+    static constexpr int NPT = 128 * NG;            // point threads
+    static constexpr int NT = NPT + 128;            // + the MMA warpgroup (its first warp issues, the others only help at the end)
+    static constexpr int UPT = 32 / NG;             // units per thread
+    static constexpr int NCH = UPT / 8;             // chunks of 8 units
+    static constexpr int GCOLS = 96 / NG;           // G columns a thread accumulates for its lane
+};
 constexpr uint32_t COL_G = 416;           // G_g, G_tg, G_t: 32 columns each
 
-template <class CF>
+template <class CF, int NG = 2>
 struct Bwd2Cfg {
+    using D = B2Dim<NG>;
     static constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
     static constexpr int CA1 = 1 + NS + (NA2 > 0 ? 1 : 0);      // A operands of MMA 1: t, g kappa_s, t g
     static constexpr int NB1 = 1 + NA2;                         // B variants of MMA 1
@@ -60,11 +71,11 @@ struct Bwd2Cfg {
     static constexpr int img_phi(int f, int part) { return 10 + 2 * f + part; }  // f: 0 t, 1 g, 2 t g
     // end-of-item scratch (floats, over the ring)
     static constexpr int RED_GD = 0;                            // [128 lanes][96]
-    static constexpr int RED_L0 = SLOT;                         // [8 warps][2][32]
-    static constexpr int RED_WL = RED_L0 + B2_NPW * 2 * 32;     // [16][256]
-    static constexpr int RED_B1 = RED_WL + 16 * B2_NPT;         // [16][256]
-    static constexpr int RED_BL = RED_B1 + 16 * B2_NPT;         // [8]
-    static constexpr int RED_KB = RED_BL + 8;                   // [max(NS,1)][32]
+    static constexpr int RED_L0 = SLOT;                         // [point warps][chunks][32]
+    static constexpr int RED_WL = RED_L0 + D::NPW * D::NCH * 32;    // [UPT][point threads]
+    static constexpr int RED_B1 = RED_WL + D::UPT * D::NPT;     // [UPT][point threads]
+    static constexpr int RED_BL = RED_B1 + D::UPT * D::NPT;     // [point warps]
+    static constexpr int RED_KB = RED_BL + D::NPW;              // [max(NS,1)][32]
     static_assert(128 * 96 <= SLOT && RED_KB + 2 * 32 <= 2 * SLOT, "reduction scratch must fit the ring");
 };
 
@@ -88,10 +99,12 @@ __device__ __forceinline__ void issue_gemm_acc(uint32_t d_tmem, uint32_t a_hi, u
     }
 }
 
-template <class CF>
-__global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
+template <class CF, int NG>
+__global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs a) {
     static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");
-    using L = Bwd2Cfg<CF>;
+    using L = Bwd2Cfg<CF, NG>;
+    using DM = B2Dim<NG>;
+    constexpr int B2_NPW = DM::NPW, B2_NPT = DM::NPT, B2_NT = DM::NT, UPT = DM::UPT, NCH = DM::NCH, GCOLS = DM::GCOLS;
     constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1, CA1 = L::CA1;
     constexpr int HH = H * H;
 
@@ -163,7 +176,7 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
         mbar_init(&bar_m3, 1);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_full[i], 64);        // the two warps of a quarter tile
+            mbar_init(&bar_full[i], 32 * NG);   // the NG warps of a quarter tile
             mbar_init(&bar_free[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,8 +189,14 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
     tc_fence_after();
     const uint32_t tbase = tmem_slot;
     const int ntiles = (count + TP - 1) / TP;
-    if (warp < B2_NPW) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // frees 112 per thread = what the two point warpgroups take
+    // registers move from the MMA warpgroup to the point warpgroups (what the former frees is what the latter take)
+    if (NG == 2) {
+        if (warp < B2_NPW) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    } else {
+        if (warp < B2_NPW) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    }
 
     float* red = sm + L::OFF_RING;            // end-of-item scratch (the ring is free once the last G MMA has completed)
 
@@ -187,23 +206,25 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
         // =============================================================================================
         const int g = warp >> 2, q = warp & 3;
         const int r = tid & 127;                    // point row of the tile = TMEM lane
-        const int j0 = 16 * g;
+        const int j0 = UPT * g;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const int slot = q & 1;
-        float* ring = sm + L::OFF_RING + slot * L::SLOT + (lane >> 2) * (int)(GK_LBO / 4) + (lane & 3) + 2 * g * (int)(GK_SBO / 4);
-        float wlacc[16], b1acc[16], l0acc[2] = {0.0f, 0.0f}, blacc = 0.0f;      // per-thread partial sums over the item
+        float* ring = sm + L::OFF_RING + slot * L::SLOT + (lane >> 2) * (int)(GK_LBO / 4) + (lane & 3) + NCH * g * (int)(GK_SBO / 4);
+        float wlacc[UPT], b1acc[UPT], l0acc[NCH], blacc = 0.0f;      // per-thread partial sums over the item
 #pragma unroll
-        for (int u = 0; u < 16; ++u) { wlacc[u] = 0.0f; b1acc[u] = 0.0f; }
-        float gacc[48];                             // this thread's 48 columns of its G lane, summed over the tiles
+        for (int u = 0; u < UPT; ++u) { wlacc[u] = 0.0f; b1acc[u] = 0.0f; }
 #pragma unroll
-        for (int u = 0; u < 48; ++u) gacc[u] = 0.0f;
+        for (int u = 0; u < NCH; ++u) l0acc[u] = 0.0f;
+        float gacc[GCOLS];                          // this thread's columns of its G lane, summed over the tiles
+#pragma unroll
+        for (int u = 0; u < GCOLS; ++u) gacc[u] = 0.0f;
         auto gather_g = [&](uint32_t parity) {      // add the G block of a finished tile (the MMA warp has committed it)
             mbar_wait_or_trap(&bar_gtile, parity);
             tc_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < 6; ++ch) {
+            for (int ch = 0; ch < GCOLS / 8; ++ch) {
                 uint32_t v[8];
-                tmem_ld8(tbase + lane_base + COL_G + 48 * g + 8 * ch, v);
+                tmem_ld8(tbase + lane_base + COL_G + GCOLS * g + 8 * ch, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 8; ++e) gacc[8 * ch + e] += __uint_as_float(v[e]);
@@ -271,9 +292,9 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
             load_idx(t0 + TP);
 
             // ---- L: t, g of this thread's 16 units; A operands of MMA 1 (t, g kappa_s, t g) -> tensor memory ----
-            float tt[16], gg[16];
+            float tt[UPT], gg[UPT];
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NCH; ++ch) {
                 const int jb = j0 + 8 * ch;
                 float av[CA1][8];
 #pragma unroll
@@ -318,12 +339,16 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
             tc_fence_before();
             mbar_arrive(&bar_a1);                              // A of MMA 1 written; D3 of the previous tile read
             load_val(t0 + TP);
+            // the previous tile's G block (complete before MMA 1 of this tile even starts: the tensor pipe runs in issue
+            // order) is added into registers while MMA 1 runs; this tile's G is issued after MMA 3, i.e. after every
+            // thread has passed this point
+            if (t > 0 && !(dbg & 1)) gather_g((uint32_t)((t - 1) & 1));
 
             // ---- E1: a2 -> h2, output-layer gradient partials, tanh transpose -> abar2 -> A operands of MMA 3 ---------
             mbar_wait_or_trap(&bar_m1, par);                   // all of MMA 1: a2 is final and its A operands may be overwritten
             tc_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NCH; ++ch) {
                 const int jb = j0 + 8 * ch;
                 uint32_t v[C][8];
 #pragma unroll
@@ -360,7 +385,6 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
                     tmem_st8(tbase + lane_base + L::COL_A3LO + c * 32 + jb, lo);
                 }
             }
-            if (t > 0 && !(dbg & 1)) gather_g((uint32_t)((t - 1) & 1));   // the previous tile's G, before this tile's G overwrites it
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&bar_a3);
@@ -376,7 +400,7 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
                 };
                 if (!(dbg & 4))
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
+                for (int ch = 0; ch < NCH; ++ch) {
                     uint32_t v[C][8];
 #pragma unroll
                     for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + c * 32 + j0 + 8 * ch, v[c]);
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
             mbar_wait_or_trap(&bar_m3, par);                   // all of MMA 3: its A operands may be rewritten by the next tile
             tc_fence_after();
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
+            for (int ch = 0; ch < NCH; ++ch) {
                 const int kb = j0 + 8 * ch;
                 uint32_t vt[8], vg[8], vtg[8];
                 tmem_ld8(tbase + lane_base + L::COL_D3 + kb, vt);
@@ -447,11 +471,11 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
         // ---- end of item: every partial to shared memory.  The last G MMA has completed (so has every ring store). ------
         if (ntiles > 0 && !(dbg & 1)) gather_g((uint32_t)((ntiles - 1) & 1));     // also: every ring read has completed
 #pragma unroll
-        for (int u = 0; u < 48; ++u) red[L::RED_GD + (q * 32 + lane) * 96 + 48 * g + u] = gacc[u];
+        for (int u = 0; u < GCOLS; ++u) red[L::RED_GD + (q * 32 + lane) * 96 + GCOLS * g + u] = gacc[u];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) red[L::RED_L0 + (warp * 2 + ch) * 32 + lane] = l0acc[ch];
+        for (int ch = 0; ch < NCH; ++ch) red[L::RED_L0 + (warp * NCH + ch) * 32 + lane] = l0acc[ch];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < UPT; ++u) {
             red[L::RED_WL + u * B2_NPT + tid] = wlacc[u];
             red[L::RED_B1 + u * B2_NPT + tid] = b1acc[u];
         }
@@ -562,13 +586,13 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
     __syncthreads();
 
     float* gp = a.gpart + (int64_t)item * a.P;
-    // first layer, value path: (unit k, quantity t) sits in lane (k % 8) * 4 + t of chunk (k % 16) / 8 of the four point warps
-    // of unit half k / 16
+    // first layer, value path: (unit k, quantity t) sits in lane (k % 8) * 4 + t of chunk (k % UPT) / 8 of the four point warps
+    // of unit group k / UPT
     auto l0 = [&](int k, int t) {
-        const int gg_ = k >> 4, ch = (k >> 3) & 1, ln = (k & 7) * 4 + t;
+        const int gg_ = k / UPT, ch = (k % UPT) >> 3, ln = (k & 7) * 4 + t;
         float v = 0.0f;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) v += red[L::RED_L0 + ((gg_ * 4 + qq) * 2 + ch) * 32 + ln];
+        for (int qq = 0; qq < 4; ++qq) v += red[L::RED_L0 + ((gg_ * 4 + qq) * NCH + ch) * 32 + ln];
         return v;
     };
     for (int i = tid; i < H * xd; i += B2_NT) {
@@ -593,9 +617,9 @@ __global__ void __launch_bounds__(B2_NT, 1) tc_backward_kernel2(FastArgs a) {
         gp[off + i] = v;
     }
     off += HH;
-    for (int i = tid; i < 2 * H; i += B2_NT) {      // hidden bias and output weights: sums over the 128 point threads of the unit's half
+    for (int i = tid; i < 2 * H; i += B2_NT) {      // hidden bias and output weights: sums over the 128 point threads of the unit's group
         const int j = i & 31;
-        const float* src = red + (i < H ? L::RED_B1 : L::RED_WL) + (j & 15) * B2_NPT + (j >> 4) * 128;
+        const float* src = red + (i < H ? L::RED_B1 : L::RED_WL) + (j % UPT) * B2_NPT + (j / UPT) * 128;
         float v = 0.0f;
 #pragma unroll 8
         for (int p = 0; p < 128; ++p) v += src[p];

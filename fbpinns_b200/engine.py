@@ -73,6 +73,7 @@ class Plan:
         check(lib.fbp_plan_set_kernel(self._h, mode), "fbp_plan_set_kernel")
         self.kernel = kernel
         self.forward_family = ("generic", "tiled", "tensor")[int(lib.fbp_plan_forward_family(self._h))]
+        self.reverse_family = ("generic", "tiled", "tensor")[int(lib.fbp_plan_reverse_family(self._h))]
         self.is_fast = bool(lib.fbp_plan_is_fast(self._h)) and mode != 1
         self.tile_points = int(lib.fbp_plan_tile_points(self._h))
         self.scratch_per_pair = int(lib.fbp_plan_scratch_per_pair(self._h))
@@ -226,18 +227,26 @@ def build_work_items(sub_off, m_active, tile_points, target_items, split=None):
     s = int(sub_off[-1])
     chunk0 = max(1, -(-s // max(1, target_items)))
     chunk0 = -(-chunk0 // tile_points) * tile_points
-    items, sub_item_off = [], [0]
-    for sp in range(m_all):
-        a, b = int(sub_off[sp]), int(sub_off[sp + 1])
-        cnt = b - a
-        if cnt > 0:
-            parts = -(-cnt // chunk0)
-            ntiles = -(-cnt // tile_points)
-            for k, nt in enumerate(_split_tiles(ntiles, min(parts, ntiles), split)):
-                c = min(nt * tile_points, b - a)
-                items.append((sp, a, c, k))
-                a += c
-        sub_item_off.append(len(items))
+    cnts = np.diff(sub_off)
+    parts_all = np.minimum(-(-cnts // chunk0), -(-cnts // tile_points))
+    if split == "equal" and (parts_all <= 1).all():
+        # common large-problem case, vectorised: one work item per non-empty subdomain
+        nz = np.nonzero(cnts > 0)[0]
+        items = np.stack([nz, sub_off[:-1][nz], cnts[nz], np.zeros_like(nz)], axis=1)
+        sub_item_off = np.concatenate([[0], np.cumsum(cnts > 0)])
+    else:
+        items, sub_item_off = [], [0]
+        for sp in range(m_all):
+            a, b = int(sub_off[sp]), int(sub_off[sp + 1])
+            cnt = b - a
+            if cnt > 0:
+                parts = -(-cnt // chunk0)
+                ntiles = -(-cnt // tile_points)
+                for k, nt in enumerate(_split_tiles(ntiles, min(parts, ntiles), split)):
+                    c = min(nt * tile_points, b - a)
+                    items.append((sp, a, c, k))
+                    a += c
+            sub_item_off.append(len(items))
     items = np.asarray(items, dtype=np.int32).reshape(-1, 4)
     sub_item_off = np.asarray(sub_item_off, dtype=np.int32)
     n_items_active = int(sub_item_off[m_active])

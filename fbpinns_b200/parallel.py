@@ -297,7 +297,7 @@ def replicate_rows(rows, owned_idx, n, group=None):
 # --------------------------------------------------------------------------------------------------- update inputs / step
 
 def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, constraints_global, constraint_offsets,
-                              jets, layer_sizes, kernel="auto", activation="tanh", replicated=False):
+                              jets, layer_sizes, kernel="auto", activation="tanh", replicated=False, plans=None):
     """Sharded counterpart of trainers.get_update_inputs: the global active-set algebra is identical on every rank
     (every rank holds the full point set and the full static decomposition — both small), then takes are built for
     this rank's block of subdomains over the points inside them."""
@@ -332,6 +332,7 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
     out.pos_of_model, out.training_ips, out.d, out.x_batch = pos_loc, training_ips, d_stat, x_batch
     out.constraints, out.takess, out.evaluators, out.weights, out.halos = [], [], [], [], []
     out.replicated, out.owned_global, out.n_constraint = bool(replicated), [], []
+    out.kernel_point_rows = []          # rows of each constraint's global arrays behind this rank's kernel points
     sorted_all = np.sort(all_ims)
     for ic in range(len(constraints_global)):
         a, b = int(bounds[ic]), int(bounds[ic + 1])
@@ -350,7 +351,8 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
         halo = build_halo_lists(np.stack(inside), shard.rank)
         lips = torch.as_tensor(halo["local_ips"].astype(np.int32), dtype=torch.int32, device=dev)
         x_loc = gather_rows(x_ic, lips)
-        plan = Plan(layer_sizes, jets[ic], kernel=kernel, activation=activation)
+        out.kernel_point_rows.append(local[lips.long()].contiguous())
+        plan = plans[ic] if plans is not None else Plan(layer_sizes, jets[ic], kernel=kernel, activation=activation)
         takes = DeviceTakes(dd, x_loc, pos_loc, all_loc, len(a_loc), tile_points=plan.tile_points)
         ev = ConstraintEvaluator(plan, takes, x_loc, dd)
         sev = ShardedEvaluator(ev, halo, shard)

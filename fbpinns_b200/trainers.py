@@ -55,7 +55,7 @@ class UpdateInputs:
 
 
 def get_update_inputs(active, all_params, dd, x_batch_global, constraints_global, constraint_offsets,
-                      jets, layer_sizes, kernel="auto", activation="tanh"):
+                      jets, layer_sizes, kernel="auto", activation="tanh", plans=None):
     """Device implementation of FBPINNTrainer._get_x_batch + _get_update_inputs (index side).
     constraints_global[ic] = list of per-point CUDA tensors of constraint ic (first is its x_batch)."""
     m = dd.m
@@ -75,11 +75,12 @@ def get_update_inputs(active, all_params, dd, x_batch_global, constraints_global
     ips_host = training_ips.cpu().numpy().astype(np.int64)
     sizes = [c_[0].shape[0] for c_ in constraints_global]
     bounds = np.searchsorted(ips_host, np.concatenate([constraint_offsets, [constraint_offsets[-1] + sizes[-1]]]))
-    constraint_ips, constraints = [], []
+    constraint_ips, constraints, local_idx = [], [], []
     for ic in range(len(constraints_global)):
         a, b = int(bounds[ic]), int(bounds[ic + 1])
         constraint_ips.append(np.arange(a, b))
         local = (training_ips[a:b] - int(constraint_offsets[ic])).contiguous()
+        local_idx.append(local)
         constraints.append([gather_rows(c_, local) if c_.dtype == torch.float32 else c_[local.long()]
                             for c_ in constraints_global[ic]])
 
@@ -91,8 +92,10 @@ def get_update_inputs(active, all_params, dd, x_batch_global, constraints_global
     out.active, out.active_ims, out.fixed_ims, out.all_ims, out.pos_of_model = active2, active_ims, fixed_ims, all_ims, pos
     out.x_batch, out.constraints, out.training_ips, out.constraint_ips, out.d = x_batch, constraints, training_ips, constraint_ips, d_stat
     out.takess, out.evaluators = [], []
+    out.constraint_local_idx = local_idx            # rows of each constraint's global arrays that are training points now
     for ic, con in enumerate(constraints):
-        plan = Plan(layer_sizes, jets[ic], kernel=kernel, activation=activation)
+        # plans are static (network shape + jet set): the trainer hands in its own so that an active-set change creates none
+        plan = plans[ic] if plans is not None else Plan(layer_sizes, jets[ic], kernel=kernel, activation=activation)
         takes = DeviceTakes(dd, con[0], pos, all_ims, len(active_ims), tile_points=plan.tile_points)
         out.takess.append(takes)
         out.evaluators.append(ConstraintEvaluator(plan, takes, con[0], dd))
@@ -104,7 +107,7 @@ def get_update_inputs(active, all_params, dd, x_batch_global, constraints_global
 class UpdateStep:
     """One FBPINN_update (fbpinns/trainers.py:285-296) for a fixed active set, optionally captured as a CUDA graph."""
 
-    def __init__(self, inputs, params, adam, all_params, prob_flat, problem, use_cuda_graph=True):
+    def __init__(self, inputs, params, adam, all_params, prob_flat, problem, use_cuda_graph=True, affine_global=None):
         self.inp, self.params, self.adam = inputs, params, adam
         self.all_params, self.prob_flat, self.problem = all_params, prob_flat, problem
         dev = params.device
@@ -122,12 +125,19 @@ class UpdateStep:
         self.kernel_launches_per_step = None
         # constraining operators that are affine in u (all hard-BC ansatzes of the reference problems) get static
         # coefficient jets, computed once here; anything else goes through the generic nested-jvp path every step
+        # `affine_global[ic]` (FBPINNTrainer.setup): the same jets computed ONCE for all points of the constraint; an
+        # active-set change then only gathers the rows of the current training points
         self.affine = []
-        for ev, con in zip(inputs.evaluators, inputs.constraints):
+        for ic, (ev, con) in enumerate(zip(inputs.evaluators, inputs.constraints)):
             base = ev.ev if hasattr(ev, "ev") else ev             # sharded evaluators wrap the local one
             aff = None
             if self.has_constraining and prob_flat is None and base.takes.npou == 1:
-                aff = AffineConstraining.build(base.plan.jet, base.x, problem.constraining_fn, all_params)
+                rows = getattr(inputs, "kernel_point_rows", None)
+                if affine_global is not None and rows is not None:
+                    ag = affine_global[ic]
+                    aff = None if ag is None else AffineConstraining(ag.jet, gather_rows(ag.Aj, rows[ic]), gather_rows(ag.Bj, rows[ic]))
+                else:
+                    aff = AffineConstraining.build(base.plan.jet, base.x, problem.constraining_fn, all_params)
             base.set_affine(aff)            # fused into the reduce kernels (forward Leibniz rule and its transpose)
             self.affine.append(aff)
 
@@ -321,6 +331,17 @@ class FBPINNTrainer(_Trainer):
             self.u_exact = None
         self._test_eval = None
         self.all_params = all_params
+        # static across active-set changes: one plan per constraint, and the jets of an affine constraining operator
+        # A(x) u + B(x) at EVERY point of the constraint (an active-set change gathers rows instead of re-deriving them)
+        self.plans = [Plan(self.layer_sizes, j, kernel=c.kernel, activation=self.activation) for j in self.jets]
+        from .problems import Problem
+        self.affine_global = None
+        if problem.constraining_fn is not Problem.constraining_fn and self.prob_flat is None and self.dd.npou == 1:
+            self.affine_global = [AffineConstraining.build(j, con[0], problem.constraining_fn, all_params)
+                                  for j, con in zip(self.jets, self.constraints_global)]
+            for ag in self.affine_global:
+                if ag is not None:
+                    ag.Aj, ag.Bj = ag.Aj.contiguous().float(), ag.Bj.contiguous().float()
         self.n_rebuilds = 0
         self.inputs = self.update = None
         return self
@@ -334,9 +355,10 @@ class FBPINNTrainer(_Trainer):
         if shard is None or shard.world == 1:
             self.inputs = get_update_inputs(active, self.all_params, self.dd, self.x_batch_global, self.constraints_global,
                                             self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel,
-                                            activation=self.activation)
+                                            activation=self.activation, plans=self.plans)
+            self.inputs.kernel_point_rows = self.inputs.constraint_local_idx
             self.update = UpdateStep(self.inputs, self.params, self.adam, self.all_params, self.prob_flat, c.problem,
-                                     c.use_cuda_graph)
+                                     c.use_cuda_graph, affine_global=self.affine_global)
         else:
             from . import parallel
             # several constraints or trainables of the problem itself: evaluate loss_fn on the full ujs on every rank
@@ -344,10 +366,10 @@ class FBPINNTrainer(_Trainer):
             self.inputs = parallel.get_update_inputs_sharded(shard, active, self.all_params, self.dd, self.x_batch_global,
                                                              self.constraints_global, self.constraint_offsets, self.jets,
                                                              self.layer_sizes, kernel=c.kernel, activation=self.activation,
-                                                             replicated=replicated)
+                                                             replicated=replicated, plans=self.plans)
             self.update = parallel.make_sharded_update(UpdateStep)(shard, self.inputs, self.params, self.adam,
                                                                    self.all_params, self.prob_flat, c.problem,
-                                                                   c.use_cuda_graph)
+                                                                   c.use_cuda_graph, affine_global=self.affine_global)
         self.n_rebuilds += 1
         torch.cuda.synchronize()
         logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs done ({time.time() - t0:.2f} s); "

@@ -130,6 +130,7 @@ int32_t fbp_plan_tile_points(const fbp_plan* plan);       /* points per CTA tile
 int fbp_plan_set_kernel(fbp_plan* plan, int32_t mode);
 int32_t fbp_plan_has_tensor(const fbp_plan* plan);        /* 1 if mode 3 is available for this plan */
 int32_t fbp_plan_forward_family(const fbp_plan* plan);    /* family fbp_forward will use: 0 generic, 1 tiled, 2 tensor */
+int32_t fbp_plan_reverse_family(const fbp_plan* plan);    /* family fbp_backward will use: 0 generic, 1 tiled, 2 tensor */
 /* Scratch floats the generic kernels need per pair (0 for tiled plans in auto mode). */
 int64_t fbp_plan_scratch_per_pair(const fbp_plan* plan);
 /* Floats per pair of the optional activation cache (0 if the plan's kernels do not use one).  When a cache of

@@ -339,3 +339,18 @@ def test_checkpoint_is_in_the_reference_pickle_format(tmp_path):
     with ck.optax_classes():
         model = pickle.loads(raw)
     assert isinstance(model, tuple) and len(model) == 5 and type(model[2][0]).__name__ == "ScaleByAdamState" and model[2][1] == ()
+
+
+def test_xla_ffi_shim_compiles_against_stub():
+    """csrc/xla_ffi_shim.cc (the jax.ffi binding over the C ABI) cannot be built for real here (no jaxlib headers); it is at
+    least type-checked against a minimal stand-in of xla/ffi/api/ffi.h, so that its calls stay in step with
+    include/fbpinn_b200.h (argument order and count of fbp_forward / fbp_reduce_* / fbp_backward)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "tests", "tools", "xla_ffi_stub"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + cuda_inc, os.path.join(ROOT, "fbpinns_b200", "csrc", "xla_ffi_shim.cc")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-3000:]
