@@ -30,6 +30,14 @@ class PlanDesc(C.Structure):
                 ("comp_k", C.c_int32 * FBP_MAX_COMP), ("comp_l", C.c_int32 * FBP_MAX_COMP)]
 
 
+FBP_HALO_MAX_WORLD = 8
+
+
+class HaloPeers(C.Structure):
+    "fbp_halo_peers of include/fbpinn_b200.h"
+    _fields_ = [("data", C.c_void_p * FBP_HALO_MAX_WORLD), ("flags", C.c_void_p * FBP_HALO_MAX_WORLD)]
+
+
 class TakesView(C.Structure):
     _fields_ = [("n", C.c_int64), ("s", C.c_int64), ("q", C.c_int64), ("s_active", C.c_int64),
                 ("m_all", C.c_int32), ("m_active", C.c_int32), ("npou", C.c_int32),
@@ -83,6 +91,9 @@ SIGNATURES = {
     "fbp_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I32, _F, _F, _F, _F, _F, _P]),
     "fbp_fma_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
     "fbp_ffma2_peak": (C.c_int, [_I32, C.POINTER(_F), _P]),
+    "fbp_halo_push": (C.c_int, [_P, _I32, _P, _P, _I32, _P, _P, _I32, _I32, _P, _P, _P]),
+    "fbp_halo_pull": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, C.c_int64, C.c_uint32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "fbp_scatter_rows": (C.c_int, [_P, _P, C.c_int64, _I32, C.c_float, _P, _P]),
     "fbp_tc_selftest": (C.c_int, [_P, _P, _P, _I32, _P]),
     "fbp_tc_selftest_g": (C.c_int, [_P, _P, _P, _I32, _P]),
 }

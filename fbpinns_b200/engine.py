@@ -22,11 +22,18 @@ from .jets import JetSpec
 I32 = torch.int32
 
 
+_DEVICE_INFO = {}
+
+
 def device_info():
-    lib = _lib.load()
-    sm, major, minor, smem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
-    check(lib.fbp_device_info(C.byref(sm), C.byref(major), C.byref(minor), C.byref(smem)), "fbp_device_info")
-    return dict(sm_count=sm.value, cc=(major.value, minor.value), smem_optin=smem.value)
+    "properties of torch's current CUDA device (cached per device ordinal: the query costs milliseconds)"
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    if dev not in _DEVICE_INFO:
+        lib = _lib.load()
+        sm, major, minor, smem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        check(lib.fbp_device_info(C.byref(sm), C.byref(major), C.byref(minor), C.byref(smem)), "fbp_device_info")
+        _DEVICE_INFO[dev] = dict(sm_count=sm.value, cc=(major.value, minor.value), smem_optin=smem.value)
+    return _DEVICE_INFO[dev]
 
 
 # --------------------------------------------------------------------------------------------------- plan

@@ -295,6 +295,12 @@ class FBPINNTrainer(_Trainer):
         sizes = [con[0].shape[0] for con in self.constraints_global]
         self.constraint_offsets = np.cumsum([0] + sizes[:-1]).astype(np.int64)
         self.jets = [JetSpec(r, xd, ud) for r in required_ujss]
+        shard = getattr(self, "shard", None)
+        if shard is not None and shard.world > 1 and os.environ.get("FBP_SHARD_BALANCE", "1") == "1":
+            # contiguous blocks of subdomains with equal PAIR counts over the full point set (fixed for the whole run, so
+            # that parameter and optimiser-state ownership never moves)
+            _, mc = self.dd.inside_count(self.x_batch_global)
+            shard.balance(mc.cpu().numpy())
         logger.info(f"Total number of constraints: {len(self.constraints_global)}")
 
         # packed parameters + problem trainables + Adam

@@ -236,6 +236,37 @@ int fbp_fma_peak(int32_t iters, float* tflops, void* stream);
 /* The same with the packed instruction fma.rn.f32x2 (SASS FFMA2, sm_100+): 16 FMAs per thread per iteration. */
 int fbp_ffma2_peak(int32_t iters, float* tflops, void* stream);
 
+/* ---- halo exchange of the sharded step over NVLink peer memory (SURVEY §8b fbp_halo_*, §8e) ---------------------------
+ * Replaces, for one node, the reference-side collective a subdomain-sharded FBPINN_model needs around its segment sums
+ * (fbpinns/trainers.py:160-170): the partial row sums of points shared across a shard boundary travel as direct stores into
+ * the owner's receive buffer, the row cotangents travel back the same way.  Every rank owns one symmetric allocation per
+ * constraint:   int32 flags[4][FBP_HALO_MAX_WORLD]  followed by the float receive regions;  `fbp_halo_peers` holds, for every
+ * rank, device pointers (valid on the CALLING GPU: cudaIpc / symmetric-memory mappings) to its flag block and data region.
+ * Both calls are asynchronous stream work, capturable in CUDA graphs; waits are bounded (trap, never a hang). */
+#define FBP_HALO_MAX_WORLD 8
+typedef struct fbp_halo_peers {
+    float* data[FBP_HALO_MAX_WORLD];      /* base of rank j's receive regions                     */
+    int32_t* flags[FBP_HALO_MAX_WORLD];   /* rank j's flags[4][FBP_HALO_MAX_WORLD], zero-initialised */
+} fbp_halo_peers;
+/* Sends rows d_send_idx[r] of d_rows (row_floats floats each) to the peers.  d_blocks[n_blocks][4] = (peer, first send-list
+ * position, end position, number of blocks of that peer): one CTA per entry.  d_dst_off[j] = float offset inside peer j's
+ * data region where this rank's rows start (position r of the send list lands at row r there).  dir 0 = forward (partial
+ * sums to the owners), 1 = reverse (cotangents back to the sharers); d_epoch[2] = exchange counters of this rank (device),
+ * d_ticket[FBP_HALO_MAX_WORLD] zero-initialised scratch. */
+int fbp_halo_push(const float* d_rows, int32_t row_floats, const int32_t* d_send_idx, const int32_t* d_blocks, int32_t n_blocks,
+                  const fbp_halo_peers* peers, const int64_t* d_dst_off, int32_t me, int32_t dir, const int32_t* d_epoch,
+                  int32_t* d_ticket, void* stream);
+/* Waits for the peers in `from_mask` and combines what they sent: mode 0: d_rows[d_tgt[i]] += sum of the receive-region rows
+ * d_src_pos[d_src_ptr[i] .. d_src_ptr[i+1]) (fixed order: deterministic), mode 1: d_rows[d_tgt[i]] = that single row.
+ * Acknowledges to the senders and advances d_epoch[dir].  MUST be called by every rank once per exchange (n_tgt may be 0). */
+int fbp_halo_pull(float* d_rows, int32_t row_floats, const int32_t* d_tgt, const int32_t* d_src_ptr, const int32_t* d_src_pos,
+                  int32_t n_tgt, const fbp_halo_peers* peers, int64_t my_off, uint32_t from_mask, int32_t me, int32_t world,
+                  int32_t dir, int32_t mode, int32_t* d_epoch, int32_t* d_done, void* stream);
+/* d_dst (n, row_floats) = scale * d_src[d_inv[row]] where d_inv[row] >= 0, else 0: the owned-row scatter (zero fill + copy +
+ * ownership weight) of the sharded reverse pass in one launch. */
+int fbp_scatter_rows(const float* d_src, const int32_t* d_inv, int64_t n, int32_t row_floats, float scale, float* d_dst,
+                     void* stream);
+
 /* Self-test of the tensor family's MMA form: d_out[128][32] = d_a[128][32] * d_w[32][32]^T computed with the same
  * tcgen05 path the mode-3 kernels use (A written row-wise into tensor memory, B through a shared-memory descriptor,
  * 3xTF32).  `variant` = 0 for the shipped conventions; bits 0-2 probe alternatives (see fbp_tc.cu). */

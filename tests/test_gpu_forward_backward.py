@@ -280,3 +280,123 @@ def test_width64_kernel_instances_match_oracle(name, small):
     for l, ((gw, gb), (rw, rb)) in enumerate(zip(got, g_layers)):
         ew, eb = common.rel_err(gw.cpu().numpy(), rw), common.rel_err(gb.cpu().numpy(), rb)
         assert ew < TOL and eb < TOL, f"{name} layer {l}: grad rel err W {ew:.2e} b {eb:.2e}"
+
+
+def _full_size_cfg5(kernel="auto"):
+    "the trainer's own setup of BASELINE config 5 at full size (device takes, evaluator, packed parameters)"
+    from fbpinns_b200.trainers import FBPINNTrainer
+    from fbpinns_b200.util.logger import logger
+    logger.setLevel("WARNING")
+    tr = FBPINNTrainer(configs.cfg5_poisson(device="cuda:0", kernel=kernel, use_cuda_graph=False)).setup()
+    tr.set_active(np.ones(tr.dd.m, dtype=int))
+    ev = tr.inputs.evaluators[0]
+    ev.set_affine(None)                 # the subdomain kernels and the quotient rule only (constraining is tested elsewhere)
+    return tr, ev
+
+
+def test_full_size_cfg5_sampled_points_match_oracle():
+    """BASELINE config 5 at FULL size (4096 subdomains, 1024 x 1024 points, 8 726 116 pairs — where the 4096-item launch
+    order, the int32 offsets and the partial tiles live): the unconstrained ujs of ~500 sampled points, each with ALL its
+    pairs, against the float64 oracle (reference-order takes restricted to those points)."""
+    from oracle import ref_model
+    from fbpinns_b200.engine import unpack_params
+    tr, ev = _full_size_cfg5()
+    t, jet = ev.takes, ev.plan.jet
+    assert t.s == 8726116 and t.n == 1024 * 1024
+    ujets = ev.forward(tr.params)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(0)
+    n = t.n
+    pts = np.unique(np.concatenate([rng.integers(0, n, 480), [0, 1023, n - 1024, n - 1],       # corners
+                                    1024 * rng.integers(0, 1024, 8), rng.integers(0, 1024, 8)]))  # edges
+    m_take, n_take, p_take, np_take, npou = t.reference_arrays()
+    sel = np.isin(n_take, pts)
+    inv = -np.ones(n, dtype=np.int64)
+    inv[pts] = np.arange(len(pts))
+    rows = np.unique(p_take[sel])                               # npou == 1: one row per point
+    rinv = -np.ones(len(np_take), dtype=np.int64)
+    rinv[rows] = np.arange(len(rows))
+    takes_s = (m_take[sel], inv[n_take[sel]], rinv[p_take[sel]], inv[np_take[rows]], npou)
+    dt = torch.float64
+    layers = [(w.cpu().to(dt), b.cpu().to(dt)) for w, b in unpack_params(ev.plan, tr.params)]
+    dparams = [torch.as_tensor(np.asarray(p.cpu() if torch.is_tensor(p) else p), dtype=dt)
+               for p in tr.all_params["static"]["decomposition"]["subdomain"]["params"]]
+    ims = torch.as_tensor(t.sub_ids.cpu().numpy().astype(np.int64))
+    dc = {"subdomain": {"params": [p[ims] for p in dparams]}}
+    lc = [(w[ims], b[ims]) for w, b in layers]
+    x = ev.x.cpu().to(dt)[torch.as_tensor(pts)]
+    ref = ref_model.fbpinn_forward(dc, lc, x, takes_s, ref_model.get_jmaps(jet.required_ujs), None, None)
+    got = jet.ujs_plain(ujets)
+    for (iu, p), g_, r_ in zip(jet.required_ujs, got, ref):
+        # the north-star metric over the WHOLE field: error of the sampled points relative to the field's largest value
+        scale = float(g_.abs().max())
+        err = float(np.max(np.abs(g_[torch.as_tensor(pts, device=g_.device)].cpu().numpy() - r_.numpy()))) / scale
+        assert err < TOL, (p, err)
+
+
+def test_full_size_cfg5_sampled_subdomain_gradients_match_oracle():
+    """Full-size config 5: the gradients of 8 sampled subdomains (corner, edge, interior, and the ones with the largest
+    gradient) for a random cotangent of the jets, against the float64 oracle evaluated on all pairs of those subdomains."""
+    from oracle import ref_model
+    from fbpinns_b200.engine import unpack_params
+    tr, ev = _full_size_cfg5()
+    t, jet = ev.takes, ev.plan.jet
+    torch.manual_seed(0)
+    ubar = torch.randn(t.n, ev.V, device="cuda")
+    g = torch.full((t.m_active, tr.params.shape[1]), float("nan"), device="cuda")
+    ev.forward(tr.params)
+    ev.backward(ubar, tr.params, g, accumulate=False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(g).all()
+    got = [(w.cpu().double().numpy(), b.cpu().double().numpy()) for w, b in unpack_params(ev.plan, g)]
+    grow = ev.grow.cpu().double()
+    sub_off = t.sub_off.cpu().numpy()
+    sp_point, sp_row = t.spair_point.cpu().numpy(), t.spair_row.cpu().numpy()
+    sub_ids = t.sub_ids.cpu().numpy()
+    x = ev.x.cpu().double()
+    dt = torch.float64
+    layers = [(w.cpu().to(dt), b.cpu().to(dt)) for w, b in unpack_params(ev.plan, tr.params)]
+    dparams = [torch.as_tensor(np.asarray(p.cpu() if torch.is_tensor(p) else p), dtype=dt)
+               for p in tr.all_params["static"]["decomposition"]["subdomain"]["params"]]
+    jmaps = ref_model.get_jmaps(tuple((0, p) for p in jet.comps))
+    gmax = np.max(np.abs(got[1][0]).reshape(t.m_active, -1), axis=1)
+    pick = list(dict.fromkeys([int(v) for v in np.argsort(-gmax)[:3]] + [0, 63, t.m_active - 1, 2093, 1105]))
+    for sp in pick:
+        im = int(sub_ids[sp])
+        a, b = int(sub_off[sp]), int(sub_off[sp + 1])
+        xs = x[sp_point[a:b]]
+        rows = torch.as_tensor(sp_row[a:b], dtype=torch.long)
+        leaves = [(w[im].clone().requires_grad_(True), bb[im].clone().requires_grad_(True)) for w, bb in layers]
+        s = b - a
+        ps_take = [p[im].expand(s, *p.shape[1:]) for p in dparams]
+        lay_take = [(w.expand(s, *w.shape), bb.expand(s, *bb.shape)) for w, bb in leaves]
+        jets = torch.cat(ref_model.get_ujs(xs, jmaps, lambda xb: (ref_model.model_inner(ps_take, lay_take, xb)[0], ())), dim=1)
+        gr = torch.autograd.grad((grow[rows] * jets).sum(), [t_ for wb in leaves for t_ in wb])
+        for l in range(len(layers)):
+            for which in (0, 1):
+                ref = gr[2 * l + which].numpy()
+                # relative to the largest entry of this parameter group over ALL subdomains (the north-star metric)
+                scale = float(np.max(np.abs(got[l][which])))
+                err = float(np.max(np.abs(got[l][which][sp] - ref))) / scale
+                assert err < TOL, (sp, l, which, err)
+
+
+def test_step_gradients_are_bit_reproducible():
+    """No float atomics on the tiled / tensor path: every partial sum is reduced in a fixed order, so two evaluations of the
+    same step give bit-identical jets and gradients (fbp_fast.cuh / fbp_tc_bwd2.cuh)."""
+    import gpu_common
+    k = common.make_case(configs.cfg5_poisson(n_sub=(6, 5), n_pts=(150, 130)), seed=2)
+    for kernel in ["auto", "tiled"]:
+        dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+        ev = inp.evaluators[0]
+        torch.manual_seed(1)
+        ubar = torch.randn(ev.takes.n, ev.V, device=params.device)
+        outs = []
+        for rep in range(3):
+            g = torch.full((max(len(inp.active_ims), 1), params.shape[1]), float("nan"), device=params.device)
+            u = ev.forward(params).clone()
+            ev.backward(ubar, params, g, accumulate=False)
+            torch.cuda.synchronize()
+            outs.append((u, g))
+        for u, g in outs[1:]:
+            assert torch.equal(u, outs[0][0]) and torch.equal(g, outs[0][1]), kernel

@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
 def _worker(rank, world, port, name, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if name.endswith("-nccl"):          # the collective transport instead of the peer-memory one (fbp_halo_*)
+        os.environ["FBP_HALO"] = "nccl"
+        name = name[:-5]
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     try:
@@ -65,6 +68,8 @@ def _worker(rank, world, port, name, q):
             if tr.prob_flat is not None:
                 pe = float((tr.prob_flat - ref.prob_flat).abs().max())
             out[graph] = (losses, perr, pe, tr.update.graph is not None, g_err)
+            halo0 = tr.inputs.evaluators[0].halo
+            assert type(halo0).__name__ == ("HaloExchange" if os.environ.get("FBP_HALO") == "nccl" else "PeerHaloExchange")
         q.put((rank, ref_losses, out, o_loss))
         dist.barrier()
         torch.cuda.synchronize()
@@ -77,7 +82,7 @@ def _worker(rank, world, port, name, q):
     os._exit(0)                  # NCCL teardown with captured graphs alive can hang (see bench.py)
 
 
-@pytest.mark.parametrize("name", ["cfg5", "cfg3", "cfg2", "cfg1"])
+@pytest.mark.parametrize("name", ["cfg5", "cfg3", "cfg2", "cfg1", "cfg5-nccl"])
 def test_sharded_step_matches_single_gpu(name):
     world = torch.cuda.device_count()
     if world < 2:

@@ -47,6 +47,24 @@ def test_halo_lists_are_consistent():
                 assert np.array_equal(a, b)
 
 
+def test_pair_count_balanced_blocks():
+    "Shard.balance: contiguous blocks with (nearly) equal pair counts, every rank at least one subdomain, same on all ranks"
+    rng = np.random.default_rng(0)
+    for world in (2, 3, 4, 8):
+        pairs = rng.integers(100, 3000, size=97)
+        pairs[:12] //= 3                          # a light edge
+        b = Shard(0, world).balance(pairs)
+        assert b[0] == 0 and b[-1] == len(pairs) and (np.diff(b) >= 1).all()
+        assert np.array_equal(b, Shard(world - 1, world).balance(pairs))
+        loads = np.array([pairs[b[j]:b[j + 1]].sum() for j in range(world)])
+        eq = np.array([pairs[(j * 97) // world:((j + 1) * 97) // world].sum() for j in range(world)])
+        assert loads.max() <= eq.max() + pairs.max()
+        assert loads.max() / loads.mean() < 1.0 + 1.5 * world * pairs.max() / pairs.sum()
+        sh = Shard(1, world)
+        sh.balance(pairs)
+        assert sh.block(len(pairs)) == (int(b[1]), int(b[2]))
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
