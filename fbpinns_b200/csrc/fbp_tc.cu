@@ -208,11 +208,11 @@ static int tc_forward_nwg(FastArgs a, int grid, cudaStream_t st) {
 
 template <class CF>
 static int tc_forward_v2(FastArgs a, int grid, cudaStream_t st) {
-    constexpr size_t bytes = sizeof(float) * FwdSmem<CF, 4>::FLOATS;
+    constexpr size_t bytes = sizeof(float) * Fwd2Smem<CF>::FLOATS;
     // the attribute belongs to the (function, device) pair and the call is cheap: set it on every launch, so that a
     // process driving several GPUs configures each of them
     FBP_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel2<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    tc_forward_kernel2<CF><<<grid, 512, bytes, st>>>(a);
+    tc_forward_kernel2<CF><<<grid, F2_NT, bytes, st>>>(a);
     FBP_LAUNCH_CHECK();
     return 0;
 }

@@ -138,6 +138,9 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // warp index as a value the compiler knows to be warp-uniform, and the single-lane election used for MMA issue:
 // with both, ptxas keeps the MMA operands in uniform registers instead of wrapping every tcgen05.mma in a
 // waterfall loop (ELECT/PLOP3/BRA per instruction when the guard is `tid == 0`)
@@ -200,6 +203,59 @@ __device__ __forceinline__ void issue_gemm_half(uint32_t d_tmem, uint32_t a_hi, 
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
             mma_tf32_ts(d_tmem, acol + ks * 8, bd + (uint64_t)((ks * 2 * B_LBO) >> 4), idesc, (pr | ks) != 0 ? 1u : 0u);
+    }
+}
+
+// hi = the value itself (the tensor core reads only the upper 19 bits), lo = what that read drops
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// 3xTF32 product of one 128 x 32 A block in tensor memory with N rows of B (canonical layout; N = 32: one matrix, N = 64:
+// two matrices stored back to back), small terms first; `fresh`: the first MMA overwrites the accumulator.  One
+// instruction per K step and product (12 in all).
+template <int N>
+__device__ __forceinline__ void issue_gemm_acc(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
+    constexpr uint32_t idesc = make_idesc_tf32(128, N);
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) {
+        const uint32_t acol = (pr == 0) ? a_lo : a_hi;
+        const uint64_t bd = (pr == 1) ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            mma_tf32_ts(d_tmem, acol + ks * 8, bd + (uint64_t)((ks * 2 * B_LBO) >> 4), idesc, (fresh && pr == 0 && ks == 0) ? 0u : 1u);
+    }
+}
+
+// The first layer is linear in the normalised point, so its jets factor per unit k: h1_0 = t, h1_s = g kappa_s[k],
+// h1_ss = -2 kappa_s[k]^2 (t g) with kappa_s[k] = W0[k][axis s] / sd.  The hidden GEMM a2 = h1 W1^T therefore needs only the
+// A operands (t, g kappa_s, t g) against W1 and, for the second-order components, W1 diag(-2 kappa_s^2):
+//   CA1 = A operands,  NB1 = B variants;  component c of a2 uses A operand fac_ia(c) and B variant fac_vb(c).
+template <class CF>
+struct Factored {
+    static constexpr int CA1 = 1 + CF::NS + (CF::NA2 > 0 ? 1 : 0);
+    static constexpr int NB1 = 1 + CF::NA2;
+    __host__ __device__ static constexpr int ia(int c) {
+        return c == 0 ? 0 : (c <= 2 * CF::NA2 ? (((c - 1) & 1) ? CA1 - 1 : 1 + ((c - 1) >> 1)) : 1 + CF::NA2 + (c - 1 - 2 * CF::NA2));
+    }
+    __host__ __device__ static constexpr int vb(int c) { return (c > 0 && c <= 2 * CF::NA2 && ((c - 1) & 1)) ? 1 + ((c - 1) >> 1) : 0; }
+};
+// Stage W1 and its scaled variants (hi, lo) as B operands B1_v[n = j][k] = W1[j][k] sc_v[k]: [NB1][hi, lo][H*H] floats at b1.
+template <class CF>
+__device__ __forceinline__ void stage_b1_variants(float* b1, const float* __restrict__ w1, const float* sm, int tid, int nthreads) {
+    for (int i = tid; i < H * H; i += nthreads) {
+        const int j = i >> 5, k = i & 31;
+        const float w = w1[i];
+#pragma unroll
+        for (int v = 0; v < Factored<CF>::NB1; ++v) {
+            float sc = 1.0f;
+            if (v > 0) {
+                const float kap = sm[CF::SM_W0D + (v - 1) * H + k];
+                sc = -2.0f * kap * kap;
+            }
+            uint32_t hi, lo;
+            tf32_split(w * sc, hi, lo);
+            b1[(2 * v) * H * H + bcore_index(j, k)] = __uint_as_float(hi);
+            b1[(2 * v + 1) * H * H + bcore_index(j, k)] = __uint_as_float(lo);
+        }
     }
 }
 
@@ -445,34 +501,44 @@ __global__ void __launch_bounds__(128 * NWG, 1) tc_forward_kernel(FastArgs a) {
 
 
 // =====================================================================================================
-// forward, software-pipelined variant (opt-in: FBP_TC_FWD=2; outputs validated on a B200 at 2.8e-7, not yet timed)
+// forward, software-pipelined kernel (the default: FBP_TC_FWD=2)
 // =====================================================================================================
-// The bring-up breakdown (profiles/r1f_tc_bringup.md) shows the first kernel paying the tensor-core time and ~0.85 ms of
-// latency serially because only one tile fits tensor memory.  Here the CTA still owns one tile's worth of TMEM, but the
-// phases of consecutive tiles are interleaved:
+// The first kernel pays the tensor-core time and ~0.85 ms of latency serially because only one tile fits tensor memory
+// (profiles/r1f_tc_bringup.md).  Here the CTA still owns one tile's worth of TMEM, but the phases of consecutive tiles are
+// interleaved:
 //     wait MMA(t)  ->  layer 0 of tile t+1 -> A   ->  read D(t) into registers  ->  barrier  ->  issue MMA(t+1)
 //                  ->  epilogue math of tile t (tanh jets, cache, output dot, window) while MMA(t+1) runs
 // A is free once MMA(t) is complete and D is free once every thread holds its accumulators, so MMA(t+1) overlaps the
-// whole epilogue of tile t.  Two CTA-wide barriers per tile instead of three (the staged output copy is private to
-// warpgroup 0), the 2-instruction TF32 split, 4 warpgroups.
+// whole epilogue of tile t.  Round 2: the A operands are the factored ones (t, g kappa_s, t g: Factored<CF>, 4 instead of 5
+// hi/lo pairs to split and store at C = 5), every product is one N = 32 (12 instructions per component instead of 24), and
+// a 17th warp issues them, so that no epilogue warp is held back by the issue loop (the MMA warpgroup hands its registers
+// to the 16 epilogue warps with setmaxnreg).
+constexpr int F2_NPT = 512, F2_NT = F2_NPT + 128;
 template <class CF>
-__global__ void __launch_bounds__(512, 1) tc_forward_kernel2(FastArgs a) {
+struct Fwd2Smem {
+    static constexpr int OFF_B1 = (CF::SM_PARAMS + 31) & ~31;                       // [NB1][hi, lo][H*H]
+    static constexpr int OFF_EXCH = OFF_B1 + Factored<CF>::NB1 * 2 * H * H;          // [3][C][TP] partial output dots of warpgroups 1..3
+    static constexpr int OFF_OUT = OFF_EXCH + 3 * CF::C * TP;                        // [TP][C] tile output in external component order
+    static constexpr int FLOATS = OFF_OUT + CF::C * TP;
+};
+
+template <class CF>
+__global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");
-    static_assert(3 * CF::C * 32 <= (int)TMEM_COLS, "A hi, A lo and D must fit the 512 TMEM columns");
-    constexpr int NWG = 4, NT = 512;
-    constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1;
-    constexpr uint32_t COL_AHI = 0, COL_ALO = C * 32, COL_D = 2 * C * 32;
-    using L = FwdSmem<CF, NWG>;
+    using FA = Factored<CF>;
+    constexpr int NWG = 4;
+    constexpr int C = CF::C, NS = CF::NS, NA2 = CF::NA2, NA1 = CF::NA1, CA1 = FA::CA1;
+    constexpr uint32_t COL_ALO = CA1 * 32, COL_D = 2 * CA1 * 32;
+    static_assert(COL_D + C * 32 <= (int)TMEM_COLS, "A hi, A lo and D must fit the 512 TMEM columns");
+    using L = Fwd2Smem<CF>;
     extern __shared__ __align__(128) float sm[];
-    __shared__ __align__(8) uint64_t mma_bar[2];
+    __shared__ __align__(8) uint64_t bar_a, bar_m;
     __shared__ uint32_t tmem_slot;
-    float* bhi = sm + L::OFF_BHI;
-    float* blo = sm + L::OFF_BLO;
     float* exch = sm + L::OFF_EXCH;
     float* outN = sm + L::OFF_OUT;
 
     const int tid = threadIdx.x, warp = warp_uniform();
-    const int g = tid >> 7, r = tid & 127;
+    const int g = (tid >> 7) & 3, r = tid & 127;
     const int jb = 8 * g;                   // this thread's 8 hidden units
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
@@ -492,11 +558,12 @@ __global__ void __launch_bounds__(512, 1) tc_forward_kernel2(FastArgs a) {
     }
     const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
     const float* prow = a.params + (int64_t)im * a.P;
-    fast_load_params<CF, NT>(sm, prow, xd, isd, a.axis, false);
-    stage_b(bhi, blo, prow + H * xd + H, H, 1, tid, NT);
+    fast_load_params<CF, F2_NT>(sm, prow, xd, isd, a.axis, false);
+    __syncthreads();
+    stage_b1_variants<CF>(sm + L::OFF_B1, prow + H * xd + H, sm, tid, F2_NT);
     if (tid == 0) {
-        mbar_init(&mma_bar[0], 1);
-        mbar_init(&mma_bar[1], 1);
+        mbar_init(&bar_a, F2_NPT);          // every epilogue thread: A(t+1) written and D(t) held in registers
+        mbar_init(&bar_m, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_proxy_async();
@@ -506,180 +573,189 @@ __global__ void __launch_bounds__(512, 1) tc_forward_kernel2(FastArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_slot;
-    const uint64_t bdesc_hi = make_smem_desc(smem_u32(bhi), B_LBO, B_SBO);
-    const uint64_t bdesc_lo = make_smem_desc(smem_u32(blo), B_LBO, B_SBO);
     const int ntiles = (count + TP - 1) / TP;
+    if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 
-    int pf_pt = 0;
-    float pf_x[3] = {0.0f, 0.0f, 0.0f};
-    auto load_idx = [&](int tt) {
-        const int t0n = tt * TP;
-        if (t0n < count) pf_pt = a.spair_point[first + t0n + (r < min(TP, count - t0n) ? r : 0)];
-    };
-    auto load_val = [&](int tt) {
-        if (tt * TP < count) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
-        }
-    };
-    auto normalise = [&](float (&z)[3]) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
-    };
-    // layer 0 + tanh jets of this thread's 8 units at z -> A (hi, lo) in tensor memory
-    auto layer0_to_tmem = [&](const float (&z)[3]) {
-        float hv[8][C];
-#pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4) {
-            const float4 w0 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + jb + 4 * q4);
-            const float4 w1 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + H + jb + 4 * q4);
-            const float4 w2 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + 2 * H + jb + 4 * q4);
-            const float4 b0 = *reinterpret_cast<const float4*>(sm + CF::SM_B0 + jb + 4 * q4);
-            float4 wd[NS > 0 ? NS : 1];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) wd[s] = *reinterpret_cast<const float4*>(sm + CF::SM_W0D + s * H + jb + 4 * q4);
-            const float w0a[4] = {w0.x, w0.y, w0.z, w0.w}, w1a[4] = {w1.x, w1.y, w1.z, w1.w};
-            const float w2a[4] = {w2.x, w2.y, w2.z, w2.w}, b0a[4] = {b0.x, b0.y, b0.z, b0.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float (&av)[C] = hv[4 * q4 + e];
-                av[0] = fmaf(w2a[e], z[2], fmaf(w1a[e], z[1], fmaf(w0a[e], z[0], b0a[e])));
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const float wv = e == 0 ? wd[s].x : (e == 1 ? wd[s].y : (e == 2 ? wd[s].z : wd[s].w));
-                    if (s < NA2) { av[1 + 2 * s] = wv; av[2 + 2 * s] = 0.0f; }
-                    else av[1 + 2 * NA2 + (s - NA2)] = wv;
-                }
-                fast_tanh_jets<CF>(av);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) tf32_split_fast(hv[e][c], hi[e], lo[e]);
-            tmem_st8(tbase + lane_base + COL_AHI + c * 32 + jb, hi);
-            tmem_st8(tbase + lane_base + COL_ALO + c * 32 + jb, lo);
-        }
-    };
-    auto issue_mma = [&]() {
-        if (warp == 0) {
+    if (warp == 16) {
+        // ---- MMA warp: tile t's products as soon as its A operands are complete and the previous D has been read ----
+        const uint32_t b1 = smem_u32(sm + L::OFF_B1);
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait_or_trap(&bar_a, (uint32_t)(t & 1));
+            tc_fence_after();
             if (elect_one()) {
-                tc_fence_after();
 #pragma unroll
-                for (int nh = 0; nh < 2; ++nh) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        issue_gemm_half(tbase + COL_D + c * 32 + nh * 16, tbase + COL_AHI + c * 32, tbase + COL_ALO + c * 32,
-                                        bdesc_hi, bdesc_lo, nh);
-                    mma_commit(&mma_bar[nh]);
+                for (int c = 0; c < C; ++c) {
+                    const int ia = FA::ia(c), vb = FA::vb(c);
+                    issue_gemm_acc<32>(tbase + COL_D + c * 32, tbase + ia * 32, tbase + COL_ALO + ia * 32,
+                                       make_smem_desc(b1 + (uint32_t)((2 * vb) * H * H * 4), B_LBO, B_SBO),
+                                       make_smem_desc(b1 + (uint32_t)((2 * vb + 1) * H * H * 4), B_LBO, B_SBO), true);
                 }
+                mma_commit(&bar_m);
             }
             __syncwarp();
         }
-    };
-
-    // ---- prologue: tile 0 into A, MMA(0) in flight; coordinates of tile 1 and the index of tile 2 on their way -----
-    float z_cur[3];
-    load_idx(0);
-    load_val(0);
-    normalise(z_cur);
-    load_idx(1);
-    load_val(1);
-    load_idx(2);
-    layer0_to_tmem(z_cur);
-    tmem_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    issue_mma();
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int t0 = t * TP;
-        const int cnt = min(TP, count - t0);
-        const uint32_t parity = (uint32_t)(t & 1);
-        const bool more = t + 1 < ntiles;
-        float z_next[3];
-        normalise(z_next);                                        // pf_x holds the coordinates of tile t+1
-        load_val(t + 2);
-        load_idx(t + 3);
-
-        mbar_wait_or_trap(&mma_bar[1], parity);                  // every MMA of tile t is complete: A is free, D is final
-        tc_fence_after();
-        if (more) layer0_to_tmem(z_next);
-        uint32_t v[C][8];
+    } else if (warp < 16) {
+        int pf_pt = 0;
+        float pf_x[3] = {0.0f, 0.0f, 0.0f};
+        auto load_idx = [&](int tt) {
+            const int t0n = tt * TP;
+            if (t0n < count) pf_pt = a.spair_point[first + t0n + (r < min(TP, count - t0n) ? r : 0)];
+        };
+        auto load_val = [&](int tt) {
+            if (tt * TP < count) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + COL_D + c * 32 + jb, v[c]);
-        tmem_wait_ld();
-        tmem_wait_st();
-        tc_fence_before();
-        __syncthreads();                                         // A(t+1) complete, D(t) held in registers everywhere
-        if (more) issue_mma();
-
-        // ---- epilogue math of tile t (the tensor core works on tile t+1 meanwhile) -----------------------------
-        float up[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) up[c] = 0.0f;
-        float* cb = nullptr;
-        int cntb = 0;
-        if (a.cache != nullptr && r < cnt) {
-            constexpr int TPB = CF::TPB;
-            const int off = t0 + r;
-            const int t0b = (off / TPB) * TPB;
-            cntb = min(TPB, count - t0b);
-            cb = a.cache + (int64_t)(first + t0b) * (H * C) + (off - t0b);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float acc[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[c] = __uint_as_float(v[c][e]);
-            acc[0] += sm[CF::SM_B1 + jb + e];
-            fast_tanh_jets<CF>(acc);
-            if (cb != nullptr) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) cb[((jb + e) * C + c) * cntb] = acc[c];
+                for (int d = 0; d < 3; ++d) pf_x[d] = d < xd ? a.x[(int64_t)pf_pt * xd + d] : 0.0f;
             }
-            const float wl = sm[CF::SM_WL + jb + e];
+        };
+        auto normalise = [&](float (&z)[3]) {
 #pragma unroll
-            for (int c = 0; c < C; ++c) up[c] = fmaf(wl, acc[c], up[c]);
-        }
-        if (g > 0) {
+            for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
+        };
+        // layer 0 of this thread's 8 units at z -> factored A operands (t, g kappa_s, t g), hi / lo, in tensor memory
+        auto layer0_to_tmem = [&](const float (&z)[3]) {
+            float av[CA1][8];
 #pragma unroll
-            for (int c = 0; c < C; ++c) exch[((g - 1) * C + c) * TP + r] = up[c];
-        }
-        __syncthreads();
-        if (g == 0) {
-            float u[C];
+            for (int q4 = 0; q4 < 2; ++q4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + jb + 4 * q4);
+                const float4 w1 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + H + jb + 4 * q4);
+                const float4 w2 = *reinterpret_cast<const float4*>(sm + CF::SM_W0 + 2 * H + jb + 4 * q4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sm + CF::SM_B0 + jb + 4 * q4);
+                float4 wd[NS > 0 ? NS : 1];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float sum = up[c];
+                for (int s = 0; s < NS; ++s) wd[s] = *reinterpret_cast<const float4*>(sm + CF::SM_W0D + s * H + jb + 4 * q4);
+                const float w0a[4] = {w0.x, w0.y, w0.z, w0.w}, w1a[4] = {w1.x, w1.y, w1.z, w1.w};
+                const float w2a[4] = {w2.x, w2.y, w2.z, w2.w}, b0a[4] = {b0.x, b0.y, b0.z, b0.w};
 #pragma unroll
-                for (int gg = 1; gg < NWG; ++gg) sum += exch[((gg - 1) * C + c) * TP + r];
-                u[c] = un_sd * (sum + (c == 0 ? sm[CF::SM_BL] : 0.0f));
-            }
-            u[0] += un_mu;
-            float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
-            fast_window<CF>(z_cur, isd, xd, flag, a.axis, w, w1, w2);
-            float* o = outN + r * C;
-            o[a.ext[0]] = u[0] * w;
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const int e = 4 * q4 + e4;
+                    const float a0 = fmaf(w2a[e4], z[2], fmaf(w1a[e4], z[1], fmaf(w0a[e4], z[0], b0a[e4])));
+                    const float tv = fbp_tanh(a0);
+                    const float gv = 1.0f - tv * tv;
+                    av[0][e] = tv;
 #pragma unroll
-            for (int s = 0; s < NA2; ++s) {
-                const float u1 = u[1 + 2 * s], u2 = u[2 + 2 * s];
-                o[a.ext[1 + 2 * s]] = u1 * w + u[0] * w1[s];
-                o[a.ext[2 + 2 * s]] = u2 * w + 2.0f * u1 * w1[s] + u[0] * w2[s];
+                    for (int s = 0; s < NS; ++s)
+                        av[1 + s][e] = gv * (e4 == 0 ? wd[s].x : (e4 == 1 ? wd[s].y : (e4 == 2 ? wd[s].z : wd[s].w)));
+                    if (NA2 > 0) av[CA1 - 1][e] = tv * gv;
+                }
             }
 #pragma unroll
-            for (int s = 0; s < NA1; ++s) {
-                const int c = 1 + 2 * NA2 + s;
-                o[a.ext[c]] = u[c] * w + u[0] * w1[NA2 + s];
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // warpgroup 0 only: the staged tile is complete
-            float* dst = a.pair_out + (int64_t)(first + t0) * C;
-            for (int i = r; i < cnt * C; i += 128) dst[i] = outN[i];
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // ... and copied before the next tile overwrites it
-        }
+            for (int i = 0; i < CA1; ++i) {
+                uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) z_cur[d] = z_next[d];
+                for (int e = 0; e < 8; ++e) {
+                    hi[e] = __float_as_uint(av[i][e]);
+                    lo[e] = __float_as_uint(tf32_lo(av[i][e]));
+                }
+                tmem_st8(tbase + lane_base + i * 32 + jb, hi);
+                tmem_st8(tbase + lane_base + COL_ALO + i * 32 + jb, lo);
+            }
+        };
+
+        // ---- prologue: tile 0 into A; coordinates of tile 1 and the index of tile 2 on their way -----------------------
+        float z_cur[3];
+        load_idx(0);
+        load_val(0);
+        normalise(z_cur);
+        load_idx(1);
+        load_val(1);
+        load_idx(2);
+        if (ntiles > 0) {
+            layer0_to_tmem(z_cur);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bar_a);
+        }
+
+        for (int t = 0; t < ntiles; ++t) {
+            const int t0 = t * TP;
+            const int cnt = min(TP, count - t0);
+            const bool more = t + 1 < ntiles;
+            float z_next[3];
+            normalise(z_next);                                        // pf_x holds the coordinates of tile t+1
+            load_val(t + 2);
+            load_idx(t + 3);
+
+            mbar_wait_or_trap(&bar_m, (uint32_t)(t & 1));            // every MMA of tile t is complete: A is free, D is final
+            tc_fence_after();
+            if (more) layer0_to_tmem(z_next);
+            uint32_t v[C][8];
+#pragma unroll
+            for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + COL_D + c * 32 + jb, v[c]);
+            tmem_wait_ld();
+            if (more) {
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&bar_a);                                  // A(t+1) complete, D(t) held in registers
+            }
+
+            // ---- epilogue math of tile t (the tensor core works on tile t+1 meanwhile) -----------------------------
+            float up[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) up[c] = 0.0f;
+            float* cb = nullptr;
+            int cntb = 0;
+            if (a.cache != nullptr && r < cnt) {
+                constexpr int TPB = CF::TPB;
+                const int off = t0 + r;
+                const int t0b = (off / TPB) * TPB;
+                cntb = min(TPB, count - t0b);
+                cb = a.cache + (int64_t)(first + t0b) * (H * C) + (off - t0b);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float acc[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = __uint_as_float(v[c][e]);
+                acc[0] += sm[CF::SM_B1 + jb + e];
+                fast_tanh_jets<CF>(acc);
+                if (cb != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) cb[((jb + e) * C + c) * cntb] = acc[c];
+                }
+                const float wl = sm[CF::SM_WL + jb + e];
+#pragma unroll
+                for (int c = 0; c < C; ++c) up[c] = fmaf(wl, acc[c], up[c]);
+            }
+            if (g > 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) exch[((g - 1) * C + c) * TP + r] = up[c];
+            }
+            asm volatile("bar.sync 2, 512;" ::: "memory");           // the 16 epilogue warps: partial dots exchanged
+            if (g == 0) {
+                float u[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float sum = up[c];
+#pragma unroll
+                    for (int gg = 1; gg < NWG; ++gg) sum += exch[((gg - 1) * C + c) * TP + r];
+                    u[c] = un_sd * (sum + (c == 0 ? sm[CF::SM_BL] : 0.0f));
+                }
+                u[0] += un_mu;
+                float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
+                fast_window<CF>(z_cur, isd, xd, flag, a.axis, w, w1, w2);
+                float* o = outN + r * C;
+                o[a.ext[0]] = u[0] * w;
+#pragma unroll
+                for (int s = 0; s < NA2; ++s) {
+                    const float u1 = u[1 + 2 * s], u2 = u[2 + 2 * s];
+                    o[a.ext[1 + 2 * s]] = u1 * w + u[0] * w1[s];
+                    o[a.ext[2 + 2 * s]] = u2 * w + 2.0f * u1 * w1[s] + u[0] * w2[s];
+                }
+#pragma unroll
+                for (int s = 0; s < NA1; ++s) {
+                    const int c = 1 + 2 * NA2 + s;
+                    o[a.ext[c]] = u[c] * w + u[0] * w1[NA2 + s];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // warpgroup 0 only: the staged tile is complete
+                float* dst = a.pair_out + (int64_t)(first + t0) * C;
+                for (int i = r; i < cnt * C; i += 128) dst[i] = outN[i];
+            }
+            // warpgroups 1-3 may overwrite `exch` for the next tile only after warpgroup 0 has read it
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+#pragma unroll
+            for (int d = 0; d < 3; ++d) z_cur[d] = z_next[d];
+        }
     }
     tc_fence_before();
     __syncthreads();

@@ -79,26 +79,6 @@ struct Bwd2Cfg {
     static_assert(128 * 96 <= SLOT && RED_KB + 2 * 32 <= 2 * SLOT, "reduction scratch must fit the ring");
 };
 
-// hi = the value itself (the tensor core reads only the upper 19 bits), lo = what that read drops
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-
-// 3xTF32 product of one 128 x 32 A block in tensor memory with N rows of B (canonical layout; N = 32: one matrix, N = 64:
-// two matrices stored back to back), small terms first; `fresh`: the first MMA overwrites the accumulator.  One
-// instruction per K step and product (12 in all): the single issuing thread, not the tensor pipe, is what N = 16 halves
-// would saturate.
-template <int N>
-__device__ __forceinline__ void issue_gemm_acc(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo, bool fresh) {
-    constexpr uint32_t idesc = make_idesc_tf32(128, N);
-#pragma unroll
-    for (int pr = 0; pr < 3; ++pr) {
-        const uint32_t acol = (pr == 0) ? a_lo : a_hi;
-        const uint64_t bd = (pr == 1) ? b_lo : b_hi;
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-            mma_tf32_ts(d_tmem, acol + ks * 8, bd + (uint64_t)((ks * 2 * B_LBO) >> 4), idesc, (fresh && pr == 0 && ks == 0) ? 0u : 1u);
-    }
-}
-
 template <class CF, int NG>
 __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs a) {
     static_assert(CF::H == 32 && CF::NHID == 2, "tensor family: H = 32, two hidden layers");

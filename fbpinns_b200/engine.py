@@ -300,7 +300,9 @@ class DeviceTakes:
     def set_tiling(self, tile_points, target_items=None):
         if target_items is None:
             # FBP_TARGET_ITEMS: tuning knob for A/B runs (work items the list should have at least, if possible)
-            target_items = int(os.environ.get("FBP_TARGET_ITEMS", 0)) or 8 * device_info()["sm_count"]
+            # 4 items per SM: measured on one rank's share of the 8-GPU run (512 subdomains): 738 us for the two subdomain
+            # kernels against 825 us with 8 per SM (every extra item pays ~5-13 us of prologue / epilogue)
+            target_items = int(os.environ.get("FBP_TARGET_ITEMS", 0)) or 4 * device_info()["sm_count"]
         items, sub_item_off, nia, order_fwd, order_bwd = build_work_items(self.sub_off_host, self.m_active, tile_points,
                                                                           target_items)
         dev = self.sub_ids.device

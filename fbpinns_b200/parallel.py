@@ -183,7 +183,7 @@ class PeerHaloExchange:
     the owner sums them into its rows in peer order; the reverse pass returns the cotangents the same way.  Two kernels
     per exchange instead of index_select + all_to_all_single + up to 7 index_add_ launches, no NCCL latency."""
 
-    ROWS_PER_BLOCK = 2048
+    ROWS_PER_BLOCK = 256          # rows per CTA of the push kernel (cfg 5, 2 ranks: 32 K shared rows -> 128 CTAs)
 
     def __init__(self, halo, shard, device, row_floats_max):
         import torch.distributed._symmetric_memory as symm_mem

@@ -89,27 +89,32 @@ def _oracle_curve(k, n_steps, dtype):
     return np.array(losses), al, pt
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
 def test_loss_curve_matches_oracle(name):
     import gpu_common
     from test_gpu_forward_backward import _make_step
     small = dict(configs.SMALL[name])
     if name == "cfg3":
         small.update(n_sub=(4, 4), n_pts=(40, 40), line_scheduler=False)
+    if name == "cfg4":          # reduced grid, but the BASELINE network width (H = 64 tiled instance, second-order jets in 3D)
+        small.update(n_sub=(2, 2, 2), n_pts=(8, 8, 8), layer_sizes=(3, 64, 64, 1))
+    if name == "cfg5":          # the tensor (tcgen05) family: full 128-pair tiles and partial tails
+        small.update(n_sub=(4, 4), n_pts=(64, 64))
+    n_steps = {"cfg4": 8, "cfg5": 10}.get(name, N_STEPS)        # the float64 oracle needs seconds per step for these two
     k = common.make_case(configs.CONFIGS[name](**small), seed=0)
-    ref64, al64, pt64 = _oracle_curve(k, N_STEPS, torch.float64)
+    ref64, al64, pt64 = _oracle_curve(k, n_steps, torch.float64)
     for graph in [False, True]:
         dd, inp, params = gpu_common.device_case(k, kernel="auto")
         step, adam, prob_flat = _make_step(k, inp, params, params.device, graph=graph)
         got = []
-        for _ in range(N_STEPS):
+        for _ in range(n_steps):
             got.append(float(step().item()))
         got = np.array(got)
         err = np.max(np.abs(got - ref64) / np.abs(ref64))
         assert err < CURVE_TOL, f"{name} graph={graph}: loss curve deviates {err:.2e}\n{got}\n{ref64}"
-        assert int(adam.count.item()) == N_STEPS
+        assert int(adam.count.item()) == n_steps
         if graph:
-            assert step.graph is not None
+            assert step.graph is not None or n_steps < 5
         if prob_flat is not None:
             for i, kk in enumerate(pt64):
                 assert abs(prob_flat.detach().cpu().numpy()[i] - pt64[kk]) < 1e-4
