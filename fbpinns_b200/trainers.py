@@ -358,6 +358,10 @@ class FBPINNTrainer(_Trainer):
         t0 = time.time()
         logger.info(f"[i: {i}/{c.n_steps}] Updating active inputs..")
         shard = getattr(self, "shard", None)
+        # release the previous active set's buffers (and its captured graph) first: the caching allocator then hands the same
+        # blocks to the new takes / evaluators instead of going to cudaMalloc for a second copy
+        self.update = None
+        self.inputs = None
         if shard is None or shard.world == 1:
             self.inputs = get_update_inputs(active, self.all_params, self.dd, self.x_batch_global, self.constraints_global,
                                             self.constraint_offsets, self.jets, self.layer_sizes, kernel=c.kernel,

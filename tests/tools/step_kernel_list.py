@@ -25,7 +25,8 @@ kw = {}
 if "--shape" in sys.argv:
     a, b, c_, d = (int(v) for v in sys.argv[sys.argv.index("--shape") + 1].split(","))
     kw = dict(n_sub=(a, b), n_pts=(c_, d))
-c = configs.cfg5_poisson(device=f"cuda:{local}", use_cuda_graph=False, **kw)
+graph = "--graph" in sys.argv        # profile a CUDA-graph replay (what the bench times) instead of eager launches
+c = configs.cfg5_poisson(device=f"cuda:{local}", use_cuda_graph=graph, **kw)
 tr = FBPINNTrainer(c)
 if world > 1:
     from fbpinns_b200.parallel import shard_trainer
@@ -41,7 +42,8 @@ from torch.profiler import profile, ProfilerActivity   # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     tr.step()
     torch.cuda.synchronize()
-if rank == 0:
+show = int(os.environ.get("LIST_RANK", 0))
+if rank == show:
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     tot = 0.0
