@@ -305,7 +305,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and args.config == "cfg5" and not args.small:
         try:
-            traffic = json.load(open(tpath)).get(bwd_kernel)
+            tj = json.load(open(tpath))
+            traffic = next((v for k_, v in tj.items() if k_.split("::")[-1].split("(")[0] == bwd_kernel), None)
         except Exception:
             traffic = None
     peaks = {}
