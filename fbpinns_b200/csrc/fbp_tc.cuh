@@ -517,8 +517,8 @@ constexpr int F2_NPT = 512, F2_NT = F2_NPT + 128;
 template <class CF>
 struct Fwd2Smem {
     static constexpr int OFF_B1 = (CF::SM_PARAMS + 31) & ~31;                       // [NB1][hi, lo][H*H]
-    static constexpr int OFF_EXCH = OFF_B1 + Factored<CF>::NB1 * 2 * H * H;          // [3][C][TP] partial output dots of warpgroups 1..3
-    static constexpr int OFF_OUT = OFF_EXCH + 3 * CF::C * TP;                        // [TP][C] tile output in external component order
+    static constexpr int OFF_EXCH = OFF_B1 + Factored<CF>::NB1 * 2 * H * H;          // [2][3][C][TP] partial output dots of warpgroups 1..3, by tile parity
+    static constexpr int OFF_OUT = OFF_EXCH + 2 * 3 * CF::C * TP;                    // [TP][C] tile output in external component order
     static constexpr int FLOATS = OFF_OUT + CF::C * TP;
 };
 
@@ -717,9 +717,10 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) up[c] = fmaf(wl, acc[c], up[c]);
             }
+            float* ex = exch + (t & 1) * 3 * C * TP;                 // double buffered: one barrier per tile is enough
             if (g > 0) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) exch[((g - 1) * C + c) * TP + r] = up[c];
+                for (int c = 0; c < C; ++c) ex[((g - 1) * C + c) * TP + r] = up[c];
             }
             asm volatile("bar.sync 2, 512;" ::: "memory");           // the 16 epilogue warps: partial dots exchanged
             if (g == 0) {
@@ -728,7 +729,7 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
                 for (int c = 0; c < C; ++c) {
                     float sum = up[c];
 #pragma unroll
-                    for (int gg = 1; gg < NWG; ++gg) sum += exch[((gg - 1) * C + c) * TP + r];
+                    for (int gg = 1; gg < NWG; ++gg) sum += ex[((gg - 1) * C + c) * TP + r];
                     u[c] = un_sd * (sum + (c == 0 ? sm[CF::SM_BL] : 0.0f));
                 }
                 u[0] += un_mu;
@@ -750,9 +751,8 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");      // warpgroup 0 only: the staged tile is complete
                 float* dst = a.pair_out + (int64_t)(first + t0) * C;
                 for (int i = r; i < cnt * C; i += 128) dst[i] = outN[i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");      // ... and copied before the next tile overwrites it
             }
-            // warpgroups 1-3 may overwrite `exch` for the next tile only after warpgroup 0 has read it
-            asm volatile("bar.sync 2, 512;" ::: "memory");
 #pragma unroll
             for (int d = 0; d < 3; ++d) z_cur[d] = z_next[d];
         }
