@@ -304,18 +304,66 @@ class ShardedEvaluator:
     def __init__(self, ev: ConstraintEvaluator, halo, shard):
         self.ev, self.shard = ev, shard
         dev = ev.x.device
-        self.halo = make_halo_exchange(halo, shard, dev, max(ev.V, ev.plan.jet.C))
+        self.halo = make_halo_exchange(halo, shard, dev, max(ev.V, ev.plan.jet.C) * int(ev.takes.npou))
         self.owned_idx = torch.as_tensor(np.nonzero(halo["owned_local"])[0], dtype=torch.long, device=dev)
         inv = -np.ones(len(halo["owned_local"]), dtype=np.int32)
         inv[halo["owned_local"]] = np.arange(int(halo["owned_local"].sum()), dtype=np.int32)
         self.owned_inv = torch.as_tensor(inv, dtype=torch.int32, device=dev)
         t = ev.takes
-        if not (t.q == t.n and t.npou == 1):
-            raise NotImplementedError("sharded evaluation needs one row per local point (npou == 1)")
+        self.npou = int(t.npou)
         self.nsum = torch.empty((max(t.q, 1), ev.V), dtype=torch.float32, device=dev)[:t.q]
-        # denominators: local partial -> total on the owners (once per active-set change)
-        self.halo.forward_add(ev.dsum[:t.q])          # collective: every rank calls it, even with no rows
+        if self.npou == 1:
+            if t.q != t.n:
+                raise _lib.FbpError("sharded evaluation: a single partition of unity must give one row per local point")
+            # denominators: local partial -> total on the owners (once per active-set change)
+            self.halo.forward_add(ev.dsum[:t.q])          # collective: every rank calls it, even with no rows
+        else:
+            self._setup_multilevel()
         self._split_work_list()
+
+    # ---- multilevel decompositions (npou > 1): rows are (point, level) pairs and the owner of a point may hold no row for a
+    # level its own subdomains do not cover there.  Rows are therefore exchanged through a DENSE per-point layout
+    # (n_local, npou, V) (zeros where this rank has no row), and the owner applies the per-level quotient rule and the average
+    # over levels (fbpinns/trainers.py:160-170) on that layout in torch (differentiable; this path is about function, the
+    # single-level path is the tuned one).
+    def _setup_multilevel(self):
+        ev, t = self.ev, self.ev.takes
+        dev = ev.x.device
+        m_take, n_take, p_take, np_take, npou = t.reference_arrays()
+        pou_ids = ev.decomp.pou_host[t.sub_ids.cpu().numpy()]                    # level id of every local subdomain
+        levels = np.unique(ev.decomp.pou_host)
+        assert len(levels) == npou
+        row_level = np.zeros(t.q, dtype=np.int64)
+        row_level[p_take] = np.searchsorted(levels, pou_ids[m_take])
+        self.dense_idx = torch.as_tensor(np_take.astype(np.int64) * npou + row_level, dtype=torch.long, device=dev)
+        C = ev.plan.jet.C
+        dd = torch.zeros((t.n * npou, C), dtype=torch.float32, device=dev)
+        dd.index_copy_(0, self.dense_idx, ev.dsum[:t.q])
+        dd = dd.view(t.n, npou * C)
+        self.halo.forward_add(dd)
+        self.dsum_dense_owned = dd.index_select(0, self.owned_idx).view(-1, npou, C).contiguous()
+        self.overlap = False
+
+    def quotient(self, nd):
+        "owned dense numerator jets (n_owned, npou * V) -> ujets (n_owned, V): per-level quotient rule, average over levels"
+        jet = self.ev.plan.jet
+        n, L, C, ud = nd.shape[0], self.npou, jet.C, jet.ud
+        N = nd.view(n, L, C, ud)
+        D = self.dsum_dense_owned.unsqueeze(-1)                                  # (n, L, C, 1)
+        q = [None] * C
+        d0 = D[:, :, 0]
+        for c, path in enumerate(jet.comps):
+            if len(path) == 0:
+                q[c] = N[:, :, c] / d0
+        c0 = jet.index[()]
+        for c, path in enumerate(jet.comps):
+            if len(path) == 1:
+                q[c] = (N[:, :, c] - q[c0] * D[:, :, c]) / d0
+        for c, path in enumerate(jet.comps):
+            if len(path) == 2:
+                ck, cl = jet.index[(path[0],)], jet.index[(path[1],)]
+                q[c] = (N[:, :, c] - q[ck] * D[:, :, cl] - q[cl] * D[:, :, ck] - q[c0] * D[:, :, c]) / d0
+        return torch.stack(q, dim=2).mean(dim=1).reshape(n, C * ud)
 
     def _split_work_list(self):
         """Boundary work items = items of subdomains that hold at least one row shared with another rank.  They are
@@ -370,6 +418,15 @@ class ShardedEvaluator:
             fwd(self.v_fwd_interior)                      # ... while the interior subdomains are evaluated
             row_sums()
             self.halo.forward_finish(self.nsum, pending)
+        elif self.npou > 1:
+            fwd(tv)
+            row_sums()
+            t = ev.takes
+            dense = torch.zeros((t.n * self.npou, ev.V), dtype=torch.float32, device=ev.x.device)
+            dense.index_copy_(0, self.dense_idx, self.nsum)
+            dense = dense.view(t.n, self.npou * ev.V)
+            self.halo.forward_add(dense)
+            return dense.index_select(0, self.owned_idx)          # (n_owned, npou * V): quotient() follows outside
         else:
             fwd(tv)
             row_sums()
@@ -383,6 +440,20 @@ class ShardedEvaluator:
         lib = _lib.load()
         ev = self.ev
         tv = ev.takes.view()
+        if self.npou > 1:
+            # cotangent of the dense numerators of the owned points -> all local points -> back to the sharers -> rows
+            t = ev.takes
+            W = self.npou * ev.V
+            gd = torch.empty((t.n, W), dtype=torch.float32, device=ev.x.device)
+            src = ujets_bar_owned.contiguous().float()
+            check(lib.fbp_scatter_rows(ptr(src), ptr(self.owned_inv), t.n, W, float(weight), ptr(gd), stream_ptr()),
+                  "fbp_scatter_rows")
+            self.halo.backward_return(gd)
+            ev.grow[:t.q].copy_(gd.view(t.n * self.npou, ev.V).index_select(0, self.dense_idx))
+            check(lib.fbp_backward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(params), ptr(ev.decomp.sub_static),
+                                   ptr(ev.grow), ptr(grads), 1, ptr(ev.gpart), ptr(ev.scratch), ev.scratch_floats,
+                                   ptr(ev.cache), stream_ptr()), "fbp_backward")
+            return
         # cotangent of every local point: the owned ones scaled by the ownership weight, zero for the others (one launch)
         ub = torch.empty((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
         src = ujets_bar_owned.contiguous().float()
@@ -419,7 +490,8 @@ class _ShardedSum(torch.autograd.Function):
 
 
 def sharded_sum(sev, params, grads, tape_hook, weight):
-    return _ShardedSum.apply(tape_hook, sev, params, grads, weight)
+    out = _ShardedSum.apply(tape_hook, sev, params, grads, weight)
+    return sev.quotient(out) if sev.npou > 1 else out
 
 
 class _ReplicateRows(torch.autograd.Function):
@@ -453,8 +525,6 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
     this rank's block of subdomains over the points inside them."""
     from .trainers import UpdateInputs, active_set_algebra
     m = dd.m
-    if dd.npou != 1:
-        raise NotImplementedError("sharding supports a single partition of unity (RectangularDecompositionND)")
     active = np.array(active).copy()
     dev = dd.device
     ims1 = torch.as_tensor(np.arange(m, dtype=np.int32)[active == 1], dtype=torch.int32, device=dev)
@@ -530,9 +600,11 @@ def make_sharded_update(base_cls):
 
         def forward_loss(self):
             self._refresh_problem_views()
-            cons = []
+            cons, owned_nothing, tape = [], False, []
             for ic, (sev, con, w, aff) in enumerate(zip(self.inp.evaluators, self.inp.constraints, self.inp.weights, self.affine)):
                 ujets = sharded_sum(sev, self.params, self.grads, self.hook, w)
+                tape.append(ujets)
+                owned_nothing = owned_nothing or (not self.inp.replicated and ujets.shape[0] == 0)
                 if self.inp.replicated:
                     ujets = replicate_rows(ujets, self.inp.owned_global[ic], self.inp.n_constraint[ic], self.shard.group)
                 jet = sev.ev.plan.jet
@@ -543,6 +615,11 @@ def make_sharded_update(base_cls):
                 else:
                     ujs = jet.ujs_plain(ujets)
                 cons.append(list(con) + ujs)
+            if owned_nothing:
+                # "weighted" mode on a rank that owns no point of a constraint (e.g. every point also lies in a subdomain of a
+                # lower rank): its share of the loss is zero — a mean over an empty set would be NaN.  The zero stays attached
+                # to the tape so that the reverse pass still serves the halo exchange and this rank's subdomains.
+                return sum(u.sum() for u in tape) * 0.0
             return self.problem.loss_fn(self.all_params, cons)
 
         def _eager(self):

@@ -32,6 +32,17 @@ def _worker(rank, world, port, name, q):
                 return configs.cfg2_harmonic_oscillator_inverse(n_sub=10, n_pts=120, device=f"cuda:{rank}", use_cuda_graph=graph)
             if name == "cfg1":      # two constraints; the boundary point x = 0 is owned by rank 0 only: the others own none of it
                 return configs.cfg1_harmonic_oscillator(n_sub=9, n_pts=90, device=f"cuda:{rank}", use_cuda_graph=graph)
+            if name == "multilevel":        # two partitions of unity: rows are (point, level), exchanged in the dense layout
+                from fbpinns_b200 import decompositions
+                from fbpinns_b200.constants import get_subdomain_ws
+                xs1 = [np.linspace(-1, 1, 3), np.linspace(0, 1, 2)]
+                xs2 = [np.linspace(-1, 1, 6), np.linspace(0, 1, 4)]
+                c = configs.cfg3_burgers(n_sub=(3, 2), n_pts=(40, 30), line_scheduler=False, device=f"cuda:{rank}",
+                                         use_cuda_graph=graph)
+                c.decomposition = decompositions.MultilevelRectangularDecompositionND
+                c.decomposition_init_kwargs = dict(subdomain_xss=[xs1, xs2], subdomain_wss=[get_subdomain_ws(xs1, 2.9),
+                                                                                          get_subdomain_ws(xs2, 2.9)], unnorm=(0., 3.))
+                return c
             return configs.cfg3_burgers(n_sub=(6, 5), n_pts=(48, 40), line_scheduler=False, device=f"cuda:{rank}",
                                         use_cuda_graph=graph)
         # single-GPU reference trajectory (every rank computes the same one)
@@ -42,7 +53,7 @@ def _worker(rank, world, port, name, q):
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         import common
         from fbpinns_b200.engine import unpack_params
-        k = common.make_case(make(False), seed=0)
+        k = common.make_case(make(False), seed=0, multilevel=(name == "multilevel"))
         k.layers = [(w.cpu().numpy(), b.cpu().numpy()) for w, b in unpack_params(ref.value_plan, ref.params)]
         if ref.prob_flat is not None:
             k.prob_trainable = {kk: ref.prob_flat.detach().cpu().numpy()[i].astype(np.float32)
@@ -82,7 +93,7 @@ def _worker(rank, world, port, name, q):
     os._exit(0)                  # NCCL teardown with captured graphs alive can hang (see bench.py)
 
 
-@pytest.mark.parametrize("name", ["cfg5", "cfg3", "cfg2", "cfg1", "cfg5-nccl"])
+@pytest.mark.parametrize("name", ["cfg5", "cfg3", "cfg2", "cfg1", "cfg5-nccl", "multilevel"])
 def test_sharded_step_matches_single_gpu(name):
     world = torch.cuda.device_count()
     if world < 2:
