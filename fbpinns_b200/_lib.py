@@ -85,7 +85,7 @@ SIGNATURES = {
     "fbp_reduce_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P]),
     "fbp_reduce_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P]),
     "fbp_row_sums": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P]),
-    "fbp_reduce_rows_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P]),
+    "fbp_reduce_rows_forward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _P]),
     "fbp_backward_workspace_floats": (_I64, [_P, C.POINTER(TakesView)]),
     "fbp_backward": (C.c_int, [_P, C.POINTER(TakesView), _P, _P, _P, _P, _P, _I32, _P, _P, _I64, _P, _P]),
     "fbp_adam_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I32, _F, _F, _F, _F, _F, _P]),

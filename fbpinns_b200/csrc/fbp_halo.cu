@@ -49,10 +49,11 @@ __global__ void __launch_bounds__(HT) halo_push_kernel(const float* __restrict__
     if (threadIdx.x == 0) wait_flag(peers.flags[me] + (2 * dir + 1) * FBP_HALO_MAX_WORLD + j, e);   // j consumed my previous rows
     __syncthreads();
     float* dst = peers.data[j] + dst_off[j];
-    const int64_t n = (int64_t)(r1 - r0) * V;
-    for (int64_t i = threadIdx.x; i < n; i += HT) {
-        const int r = r0 + (int)(i / V), v = (int)(i - (int64_t)(r - r0) * V);
-        dst[(int64_t)r * V + v] = rows[(int64_t)send_idx[r] * V + v];
+    // one thread per row: consecutive threads write consecutive rows of the peer's buffer (coalesced NVLink stores)
+    for (int r = r0 + threadIdx.x; r < r1; r += HT) {
+        const float* src = rows + (int64_t)send_idx[r] * V;
+        float* d = dst + (int64_t)r * V;
+        for (int v = 0; v < V; ++v) d[v] = src[v];
     }
     __threadfence_system();
     __syncthreads();
@@ -77,12 +78,20 @@ __global__ void __launch_bounds__(HT) halo_pull_kernel(float* __restrict__ rows,
         wait_flag(peers.flags[me] + (2 * dir + 0) * FBP_HALO_MAX_WORLD + threadIdx.x, e + 1);
     __syncthreads();
     const float* buf = peers.data[me] + my_off;
-    const int64_t n = (int64_t)n_tgt * V;
-    for (int64_t i = (int64_t)blockIdx.x * HT + threadIdx.x; i < n; i += (int64_t)gridDim.x * HT) {
-        const int t = (int)(i / V), v = (int)(i - (int64_t)t * V);
-        float acc = mode == 0 ? rows[(int64_t)tgt[t] * V + v] : 0.0f;
-        for (int s = src_ptr[t]; s < src_ptr[t + 1]; ++s) acc += buf[(int64_t)src_pos[s] * V + v];
-        rows[(int64_t)tgt[t] * V + v] = acc;
+    // one thread per target row
+    for (int t = blockIdx.x * HT + threadIdx.x; t < n_tgt; t += gridDim.x * HT) {
+        float* dst = rows + (int64_t)tgt[t] * V;
+        if (mode == 1) {                                   // reverse pass: position t of the receive region is row t's value
+            const float* src = buf + (int64_t)t * V;
+            for (int v = 0; v < V; ++v) dst[v] = src[v];
+        } else {
+            const int s0 = src_ptr[t], s1 = src_ptr[t + 1];
+            for (int v = 0; v < V; ++v) {
+                float acc = dst[v];
+                for (int s = s0; s < s1; ++s) acc += buf[(int64_t)src_pos[s] * V + v];
+                dst[v] = acc;
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -133,8 +142,7 @@ int fbp_halo_pull(float* d_rows, int32_t row_floats, const int32_t* d_tgt, const
     FBP_REQUIRE(peers && d_epoch && d_done, "fbp_halo_pull: null argument");
     FBP_REQUIRE(world >= 1 && world <= FBP_HALO_MAX_WORLD, "fbp_halo_pull: world size out of range");
     FBP_REQUIRE(dir == 0 || dir == 1, "fbp_halo_pull: dir must be 0 (forward) or 1 (reverse)");
-    const int64_t n = (int64_t)n_tgt * row_floats;
-    int grid = (int)((n + HT - 1) / HT);
+    int grid = (n_tgt + HT - 1) / HT;
     grid = grid < 1 ? 1 : (grid > 592 ? 592 : grid);      // every rank runs it each exchange (it advances the epoch)
     halo_pull_kernel<<<grid, HT, 0, (cudaStream_t)stream>>>(d_rows, row_floats, d_tgt, d_src_ptr, d_src_pos, n_tgt, *peers, my_off,
                                                           from_mask, me, world, dir, mode, d_epoch, d_done);

@@ -61,9 +61,13 @@ row_sums_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_ou
 template <bool FROM_ROWS>
 __global__ void __launch_bounds__(RT)
 reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_out,
-                      const float* __restrict__ dsum, const float* __restrict__ aff, float* __restrict__ ujets) {
+                      const float* __restrict__ dsum, const float* __restrict__ aff, float* __restrict__ ujets,
+                      const int32_t* __restrict__ out_row) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= tv.n) return;
+    // sharded evaluation: only the points this rank owns are reduced, into a compact array (out_row[p] = its row, < 0: skip)
+    const int64_t po_ = out_row ? (int64_t)out_row[p] : p;
+    if (po_ < 0) return;
     const int C = pd.C, ud = pd.ud, V = C * ud;
     float acc[FBP_MAX_COMP * FBP_MAX_UD];
     for (int v = 0; v < V; ++v) acc[v] = 0.0f;
@@ -107,7 +111,7 @@ reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ p
         }
         for (int c = 0; c < C; ++c) acc[c] = o[c];
     }
-    for (int v = 0; v < V; ++v) ujets[p * V + v] = acc[v];
+    for (int v = 0; v < V; ++v) ujets[po_ * V + v] = acc[v];
 }
 
 // ---- transpose: grow[r] = A(D_r)^T ujets_bar[point(r)] / npou ---------------------------------------
@@ -274,7 +278,7 @@ int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const flo
     FBP_REQUIRE(plan && tv, "fbp_reduce_forward: null plan/takes");
     FBP_REQUIRE(d_affine == nullptr || plan->dev.ud == 1, "fbp_reduce_forward: affine constraining needs ud == 1");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<false><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_affine, d_ujets);
+    reduce_forward_kernel<false><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_affine, d_ujets, nullptr);
     FBP_LAUNCH_CHECK();
     return 0;
 }
@@ -288,11 +292,11 @@ int fbp_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_
 }
 
 int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_nsum, const float* d_dsum,
-                            const float* d_affine, float* d_ujets, void* stream) {
+                            const float* d_affine, const int32_t* d_out_row, float* d_ujets, void* stream) {
     FBP_REQUIRE(plan && tv, "fbp_reduce_rows_forward: null plan/takes");
     FBP_REQUIRE(d_affine == nullptr || plan->dev.ud == 1, "fbp_reduce_rows_forward: affine constraining needs ud == 1");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<true><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_nsum, d_dsum, d_affine, d_ujets);
+    reduce_forward_kernel<true><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_nsum, d_dsum, d_affine, d_ujets, d_out_row);
     FBP_LAUNCH_CHECK();
     return 0;
 }

@@ -431,10 +431,11 @@ class ShardedEvaluator:
             fwd(tv)
             row_sums()
             self.halo.forward_add(self.nsum)
-        ujets = torch.empty((ev.takes.n, ev.V), dtype=torch.float32, device=ev.x.device)
+        # quotient rule (+ fused affine constraining) for the OWNED points only, written compactly
+        ujets = torch.empty((int(self.owned_idx.numel()), ev.V), dtype=torch.float32, device=ev.x.device)
         check(lib.fbp_reduce_rows_forward(ev.plan.handle, C.byref(tv), ptr(self.nsum), ptr(ev.dsum), ptr(ev.affine),
-                                          ptr(ujets), stream_ptr()), "fbp_reduce_rows_forward")
-        return ujets.index_select(0, self.owned_idx)
+                                          ptr(self.owned_inv), ptr(ujets), stream_ptr()), "fbp_reduce_rows_forward")
+        return ujets
 
     def backward(self, ujets_bar_owned, params, grads, weight=1.0):
         lib = _lib.load()
@@ -589,6 +590,23 @@ def get_update_inputs_sharded(shard, active, all_params, dd, x_batch_global, con
     return out
 
 
+class ShardedLoss:
+    """The loss of a sharded step in "weighted" mode: every rank holds its share; reading the value (`item()` / `float()`)
+    sums the shares over the ranks.  Reading is a COLLECTIVE: every rank must read the same steps' losses in the same order
+    (the trainer's reporting and bench.py do)."""
+
+    def __init__(self, share, group):
+        self.share, self.group = share, group
+
+    def item(self):
+        t = self.share.detach().clone().reshape(1)
+        dist.all_reduce(t, group=self.group)
+        return t.item()
+
+    def __float__(self):
+        return float(self.item())
+
+
 def make_sharded_update(base_cls):
     """UpdateStep variant whose forward goes through the sharded evaluators and which all-reduces the loss and the
     problem-parameter gradients."""
@@ -629,21 +647,16 @@ def make_sharded_update(base_cls):
             self.grads.zero_()
             self.hook.grad = None
             loss = self.forward_loss()
-            w0 = self.inp.weights[0]
-            with torch.no_grad():
-                # the global loss is only reported: reduce it asynchronously, hidden behind the reverse kernels
-                gl = (loss.detach() * w0).reshape(1)
-                pending = dist.all_reduce(gl, group=self.shard.group, async_op=True)
             loss.backward()
-            pg = self.problem_grad()
             with torch.no_grad():
-                if pg is not None:
-                    pg = (pg * w0).contiguous()
-                    dist.all_reduce(pg, group=self.shard.group)
-                self.adam.step(self.params, self.grads, self.active_ims_dev,
-                               self.prob_flat if pg is not None else None, pg)
-                pending.wait()
-                self.loss_out.copy_(gl[0])
+                self.adam.step(self.params, self.grads, self.active_ims_dev, None, None)
+                # this rank's share of the global loss (sum over ranks of n_owned / n times the local mean); the sum over the
+                # ranks is only formed when the value is read (ShardedLoss.item): nothing in the step depends on it
+                self.loss_out.copy_(loss.detach() * self.inp.weights[0])
             return self.loss_out
+
+        def __call__(self):
+            out = base_cls.__call__(self)
+            return out if self.inp.replicated else ShardedLoss(out, self.shard.group)
 
     return ShardedUpdateStep

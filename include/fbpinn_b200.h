@@ -202,10 +202,12 @@ int fbp_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_x
 int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out,
                        const float* d_dsum, const float* d_affine, float* d_ujets, void* stream);
 /* The same in two steps, for the multi-GPU halo exchange: row sums d_nsum [q][C*ud] of the LOCAL pairs,
- * then — after the partial sums of rows shared with other ranks have been added — the quotient rule from row sums. */
+ * then — after the partial sums of rows shared with other ranks have been added — the quotient rule from row sums.
+ * d_out_row (optional): point p is written to row d_out_row[p] of d_ujets, or skipped when that is negative (a sharded host
+ * keeps only the points it owns, compactly). */
 int fbp_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_pair_out, float* d_nsum, void* stream);
 int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_nsum, const float* d_dsum,
-                            const float* d_affine, float* d_ujets, void* stream);
+                            const float* d_affine, const int32_t* d_out_row, float* d_ujets, void* stream);
 /* Transpose of the above: cotangent of ujets [n][C*ud] -> cotangent of row numerators d_grow [q][C*ud]. */
 int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_ujets_bar,
                         const float* d_dsum, const float* d_affine, float* d_grow, void* stream);
@@ -257,7 +259,7 @@ int fbp_halo_push(const float* d_rows, int32_t row_floats, const int32_t* d_send
                   const fbp_halo_peers* peers, const int64_t* d_dst_off, int32_t me, int32_t dir, const int32_t* d_epoch,
                   int32_t* d_ticket, void* stream);
 /* Waits for the peers in `from_mask` and combines what they sent: mode 0: d_rows[d_tgt[i]] += sum of the receive-region rows
- * d_src_pos[d_src_ptr[i] .. d_src_ptr[i+1]) (fixed order: deterministic), mode 1: d_rows[d_tgt[i]] = that single row.
+ * d_src_pos[d_src_ptr[i] .. d_src_ptr[i+1]) (fixed order: deterministic), mode 1: d_rows[d_tgt[i]] = row i of the receive region (d_src_* unused).
  * Acknowledges to the senders and advances d_epoch[dir].  MUST be called by every rank once per exchange (n_tgt may be 0). */
 int fbp_halo_pull(float* d_rows, int32_t row_floats, const int32_t* d_tgt, const int32_t* d_src_ptr, const int32_t* d_src_pos,
                   int32_t n_tgt, const fbp_halo_peers* peers, int64_t my_off, uint32_t from_mask, int32_t me, int32_t world,

@@ -20,8 +20,8 @@ extern "C" int emu_row_sums(const fbp_plan* plan, const fbp_takes_view* tv, cons
 }
 extern "C" int emu_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* pair_out_or_rows, int from_rows,
                                   const float* dsum, const float* aff, float* ujets) {
-    if (from_rows) for_threads(tv->n, [&] { reduce_forward_kernel<true>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets); });
-    else for_threads(tv->n, [&] { reduce_forward_kernel<false>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets); });
+    if (from_rows) for_threads(tv->n, [&] { reduce_forward_kernel<true>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets, nullptr); });
+    else for_threads(tv->n, [&] { reduce_forward_kernel<false>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets, nullptr); });
     return 0;
 }
 extern "C" int emu_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* ubar, const float* dsum,

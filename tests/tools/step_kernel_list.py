@@ -48,10 +48,13 @@ if rank == show:
     evs.sort(key=lambda e: e.time_range.start)
     tot = 0.0
     lines = []
+    prev_end = None
     for e in evs:
         dur = e.time_range.elapsed_us()
         tot += dur
-        lines.append(f"{dur:9.1f} us  {e.name[:110]}")
+        gap = (e.time_range.start - prev_end) if prev_end is not None else 0.0
+        prev_end = max(prev_end or 0, e.time_range.end)
+        lines.append(f"{dur:9.1f} us  (+{gap:6.1f} gap)  {e.name[:100]}")
     span = (evs[-1].time_range.end - evs[0].time_range.start) if evs else 0
     txt = "\n".join(lines) + f"\n--- {len(evs)} kernels, sum {tot:.1f} us, first-to-last span {span:.1f} us (eager launch, world {world})\n"
     print(txt)
