@@ -1,7 +1,7 @@
 """
-Network plug-ins (API of fbpinns/networks.py:14-68, 197-201).  The kernels implement FCN with tanh; the other
-reference networks (AdaptiveFCN, SIREN, AdaptiveSIREN, FourierFCN) are not on the hot path of any BASELINE
-config and raise NotImplementedError in the trainer.
+Network plug-ins (API of fbpinns/networks.py:14-194, 197-201): FCN (tanh; tiled FFMA2 and tensor kernel families) and the
+reference's other networks AdaptiveFCN, SIREN, AdaptiveSIREN, FourierFCN (activation variants of the generic kernel family,
+csrc/fbp_generic_act.cu).  `kernel_layers` is what the kernels see of a network.
 """
 import numpy as np
 import torch

@@ -275,6 +275,9 @@ class FBPINNTrainer(_Trainer):
         c = self.c
         np.random.seed(c.seed)
         all_params, dev = self._init_all_params()
+        if dev.type == "cuda":
+            # the C ABI launches on torch's CURRENT device and stream: make it the trainer's device
+            torch.cuda.set_device(dev)
         domain, problem, decomposition = c.domain, c.problem, c.decomposition
         m = all_params["static"]["decomposition"]["m"]
         ud, xd = all_params["static"]["problem"]["dims"]
