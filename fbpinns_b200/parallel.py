@@ -177,6 +177,51 @@ class HaloExchange:
         return rows
 
 
+def peer_halo_layout(halo, cnt, rank, rows_per_block=256):
+    """Pure index logic of the peer-memory exchange for one rank (tested on the CPU by simulating every rank,
+    tests/test_parallel_cpu.py).  halo = build_halo_lists(...)[rank]; cnt[a][b] = rows rank a sends to owner b in the
+    forward direction (the same matrix on every rank).  Receive region of rank b, in rows: [forward: senders in rank order]
+    [reverse: owners in rank order].  Returns
+      fwd_send / bwd_send   local rows to send (forward: rows owned elsewhere; reverse: owned rows others share), peers in rank order
+      rows_fwd_dst[j] / rows_bwd_dst[j]   row offset in peer j's region such that position r of the send list lands at row offset + r
+      fwd_blocks / bwd_blocks             (peer, first position, end position, blocks of that peer) per CTA of the push kernel
+      fwd_tgt, fwd_ptr, fwd_pos           owned shared rows and, CSR, the forward-region rows to add into each (senders in rank order)
+      bwd_ptr, bwd_pos                    reverse pull: row t of the reverse region is the value of send-list row t
+      fwd_mask / bwd_mask                 peers data arrives from;  my_bwd_off_rows  start of this rank's reverse region"""
+    cnt = np.asarray(cnt, dtype=np.int64)
+    w, r = cnt.shape[0], int(rank)
+    others = [j for j in range(w) if j != r]
+    fwd_total = cnt.sum(0)                                # rows rank a receives in the forward direction
+    cat = lambda parts: np.concatenate(parts).astype(np.int64) if len(parts) else np.zeros(0, dtype=np.int64)
+    fwd_send = cat([np.asarray(halo["send"][j]) for j in others])
+    bwd_send = cat([np.asarray(halo["recv"][j]) for j in others])
+    fs_off = np.concatenate([[0], np.cumsum([len(halo["send"][j]) for j in others])]).astype(np.int64)
+    bs_off = np.concatenate([[0], np.cumsum([len(halo["recv"][j]) for j in others])]).astype(np.int64)
+    rows_fwd_dst, rows_bwd_dst = np.zeros(w, dtype=np.int64), np.zeros(w, dtype=np.int64)
+    fblk, bblk = [], []
+    for k, j in enumerate(others):
+        rows_fwd_dst[j] = int(cnt[:r, j].sum()) - int(fs_off[k])                       # after the rows of lower-ranked senders
+        rows_bwd_dst[j] = int(fwd_total[j]) + int(cnt[j, :r].sum()) - int(bs_off[k])   # after j's forward region and lower owners
+        for lst, off, blk in ((halo["send"][j], fs_off, fblk), (halo["recv"][j], bs_off, bblk)):
+            n_ = len(lst)
+            nb = -(-n_ // rows_per_block)
+            for b_ in range(nb):
+                blk.append((j, int(off[k]) + b_ * rows_per_block, int(off[k]) + min(n_, (b_ + 1) * rows_per_block), nb))
+    pos_of, base = {}, 0
+    for j in others:
+        for k_, row in enumerate(halo["recv"][j]):
+            pos_of.setdefault(int(row), []).append(base + k_)
+        base += len(halo["recv"][j])
+    tg = sorted(pos_of)
+    return dict(fwd_send=fwd_send, bwd_send=bwd_send, rows_fwd_dst=rows_fwd_dst, rows_bwd_dst=rows_bwd_dst,
+                fwd_blocks=np.asarray(fblk, dtype=np.int64).reshape(-1, 4), bwd_blocks=np.asarray(bblk, dtype=np.int64).reshape(-1, 4),
+                fwd_tgt=np.asarray(tg, dtype=np.int64), fwd_ptr=np.concatenate([[0], np.cumsum([len(pos_of[t]) for t in tg])]).astype(np.int64),
+                fwd_pos=np.asarray([p for t in tg for p in pos_of[t]], dtype=np.int64),
+                bwd_ptr=np.arange(len(fwd_send) + 1), bwd_pos=np.arange(len(fwd_send)),
+                fwd_mask=sum(1 << j for j in others if len(halo["recv"][j])), bwd_mask=sum(1 << j for j in others if len(halo["send"][j])),
+                my_bwd_off_rows=int(fwd_total[r]), region_rows=int(fwd_total[r] + cnt[r].sum()))
+
+
 class PeerHaloExchange:
     """HaloExchange over NVLink peer memory (C ABI fbp_halo_push / fbp_halo_pull, csrc/fbp_halo.cu): the sender stores its
     rows straight into the owner's receive buffer (torch.distributed._symmetric_memory allocation), publishes a flag, and
@@ -212,46 +257,14 @@ class PeerHaloExchange:
             self.peers.flags[j] = int(self.hdl.buffer_ptrs[j])
             self.peers.data[j] = int(self.hdl.buffer_ptrs[j]) + 4 * self.flag_floats
         i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), dtype=torch.int32, device=device)
-        others = [j for j in range(w) if j != r]
-        # send lists (forward: my partial sums to the owners; reverse: my owned cotangents to the sharers), peers in rank order
-        self.fwd_send = i32(np.concatenate([halo["send"][j] for j in others]) if others else [])
-        self.bwd_send = i32(np.concatenate([halo["recv"][j] for j in others]) if others else [])
-        fs_off = np.concatenate([[0], np.cumsum([len(halo["send"][j]) for j in others])]).astype(np.int64)
-        bs_off = np.concatenate([[0], np.cumsum([len(halo["recv"][j]) for j in others])]).astype(np.int64)
-        self.rows_fwd_dst = np.zeros(w, dtype=np.int64)      # row offsets inside the receiver's data region (times V at call time)
-        self.rows_bwd_dst = np.zeros(w, dtype=np.int64)
-        fblk, bblk = [], []
-        for k, j in enumerate(others):
-            # forward region of owner j: senders in rank order; my rows start after those of lower ranks
-            self.rows_fwd_dst[j] = int(cnt[:r, j].sum()) - int(fs_off[k])
-            # reverse region of sharer j starts after its forward region; owners in rank order
-            self.rows_bwd_dst[j] = int(fwd_total[j]) + int(cnt[j, :r].sum()) - int(bs_off[k])
-            for lst, off, blk in ((halo["send"][j], fs_off, fblk), (halo["recv"][j], bs_off, bblk)):
-                n_ = len(lst)
-                nb = -(-n_ // self.ROWS_PER_BLOCK)
-                for b_ in range(nb):
-                    blk.append((j, int(off[k]) + b_ * self.ROWS_PER_BLOCK, int(off[k]) + min(n_, (b_ + 1) * self.ROWS_PER_BLOCK), nb))
-        self.fwd_blocks, self.n_fwd_blocks = i32(np.asarray(fblk).reshape(-1, 4)), len(fblk)
-        self.bwd_blocks, self.n_bwd_blocks = i32(np.asarray(bblk).reshape(-1, 4)), len(bblk)
-        # forward pull: every owned shared row sums its sources (positions in my forward region, senders in rank order)
-        pos_of = {}
-        base = 0
-        for j in others:
-            for k_, row in enumerate(halo["recv"][j]):
-                pos_of.setdefault(int(row), []).append(base + k_)
-            base += len(halo["recv"][j])
-        tg = sorted(pos_of)
-        self.fwd_tgt = i32(tg)
-        self.fwd_ptr = i32(np.concatenate([[0], np.cumsum([len(pos_of[t]) for t in tg])]))
-        self.fwd_pos = i32([p for t in tg for p in pos_of[t]])
-        self.fwd_mask = sum(1 << j for j in others if len(halo["recv"][j]))
-        # reverse pull: every row I share receives its owner's value (positions in my reverse region, owners in rank order)
-        self.bwd_tgt = self.fwd_send
-        nb_ = int(self.fwd_send.numel())
-        self.bwd_ptr = i32(np.arange(nb_ + 1))
-        self.bwd_pos = i32(np.arange(nb_))
-        self.bwd_mask = sum(1 << j for j in others if len(halo["send"][j]))
-        self.my_bwd_off_rows = int(fwd_total[r])
+        lay = peer_halo_layout(halo, cnt, r, self.ROWS_PER_BLOCK)
+        self.fwd_send, self.bwd_send = i32(lay["fwd_send"]), i32(lay["bwd_send"])
+        self.rows_fwd_dst, self.rows_bwd_dst = lay["rows_fwd_dst"], lay["rows_bwd_dst"]
+        self.fwd_blocks, self.n_fwd_blocks = i32(lay["fwd_blocks"]), len(lay["fwd_blocks"])
+        self.bwd_blocks, self.n_bwd_blocks = i32(lay["bwd_blocks"]), len(lay["bwd_blocks"])
+        self.fwd_tgt, self.fwd_ptr, self.fwd_pos, self.fwd_mask = i32(lay["fwd_tgt"]), i32(lay["fwd_ptr"]), i32(lay["fwd_pos"]), lay["fwd_mask"]
+        self.bwd_tgt, self.bwd_ptr, self.bwd_pos, self.bwd_mask = self.fwd_send, i32(lay["bwd_ptr"]), i32(lay["bwd_pos"]), lay["bwd_mask"]
+        self.my_bwd_off_rows = lay["my_bwd_off_rows"]
         self.epoch = torch.zeros(2, dtype=torch.int32, device=device)
         self.ticket = torch.zeros(_lib.FBP_HALO_MAX_WORLD, dtype=torch.int32, device=device)
         self.done = torch.zeros(1, dtype=torch.int32, device=device)

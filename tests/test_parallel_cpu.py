@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 from oracle import ref_takes
 from fbpinns_b200 import configs
-from fbpinns_b200.parallel import Shard, build_halo_lists, HaloExchange, replicate_rows
+from fbpinns_b200.parallel import Shard, build_halo_lists, HaloExchange, replicate_rows, peer_halo_layout
 
 
 def _geometry(world):
@@ -45,6 +45,61 @@ def test_halo_lists_are_consistent():
                 a = halos[r]["local_ips"][halos[r]["send"][j]]
                 b = halos[j]["local_ips"][halos[j]["recv"][r]]
                 assert np.array_equal(a, b)
+
+
+def test_peer_halo_layout_simulated_exchange():
+    """Index logic of the peer-memory halo exchange (fbp_halo_push / fbp_halo_pull): every rank's layout is built here and the
+    two kernels are replayed in numpy (push = rows stored at the receiver's offsets, block by block; pull = CSR sums /
+    copies): the owners must end with the full row sums, the sharers with the owners' values, and no two senders may touch
+    the same receive-region row."""
+    for world in (2, 3, 4):
+        x, mask, blocks, inside = _geometry(world)
+        halos = [build_halo_lists(inside, r) for r in range(world)]
+        cnt = np.array([[0 if j == r else len(halos[r]["send"][j]) for j in range(world)] for r in range(world)])
+        lays = [peer_halo_layout(halos[r], cnt, r, rows_per_block=37) for r in range(world)]
+        V = 3
+        pv = (np.arange(mask.shape[0])[:, None] * 0.001 + np.arange(mask.shape[1])[None, :] * 1.0 + 0.5)
+        rows, total = [], []
+        for r in range(world):
+            lo, hi = blocks[r]
+            lips = halos[r]["local_ips"]
+            loc = (mask[:, lo:hi] * pv[:, lo:hi]).sum(1)[lips]
+            rows.append(np.stack([loc, 2 * loc, -loc], 1))
+            total.append((mask * pv).sum(1)[lips])
+        region = [np.full((lays[r]["region_rows"], V), np.nan) for r in range(world)]
+        written = [np.zeros(lays[r]["region_rows"], dtype=int) for r in range(world)]
+        # forward push (every CTA of every rank), then forward pull
+        for r in range(world):
+            for j, p0, p1, nb in lays[r]["fwd_blocks"]:
+                dst = lays[r]["rows_fwd_dst"][j] + np.arange(p0, p1)
+                region[j][dst] = rows[r][lays[r]["fwd_send"][p0:p1]]
+                written[j][dst] += 1
+        for r in range(world):
+            lay = lays[r]
+            assert (written[r][:lay["my_bwd_off_rows"]] == 1).all() and (written[r][lay["my_bwd_off_rows"]:] == 0).all()
+            for t, row in enumerate(lay["fwd_tgt"]):
+                for s_ in range(lay["fwd_ptr"][t], lay["fwd_ptr"][t + 1]):
+                    rows[r][row] += region[r][lay["fwd_pos"][s_]]
+            own = halos[r]["owned_local"]
+            assert np.allclose(rows[r][own, 0], total[r][own]) and np.allclose(rows[r][own, 2], -total[r][own])
+        # reverse: owners hold g(point); push to the sharers' reverse regions, pull = copy
+        back = []
+        for r in range(world):
+            lips, own = halos[r]["local_ips"], halos[r]["owned_local"]
+            back.append(np.where(own, np.sin(lips * 0.37), 0.0)[:, None].repeat(V, 1))
+        for r in range(world):
+            for j, p0, p1, nb in lays[r]["bwd_blocks"]:
+                dst = lays[r]["rows_bwd_dst"][j] + np.arange(p0, p1)
+                region[j][dst] = back[r][lays[r]["bwd_send"][p0:p1]]
+                written[j][dst] += 1
+        for r in range(world):
+            lay = lays[r]
+            assert (written[r] == 1).all()
+            for t, row in enumerate(lay["fwd_send"]):
+                back[r][row] = region[r][lay["my_bwd_off_rows"] + lay["bwd_pos"][t]]
+            assert np.allclose(back[r][:, 0], np.sin(halos[r]["local_ips"] * 0.37))
+            assert lay["fwd_mask"] == sum(1 << j for j in range(world) if j != r and cnt[j][r]) and \
+                lay["bwd_mask"] == sum(1 << j for j in range(world) if j != r and cnt[r][j])
 
 
 def test_pair_count_balanced_blocks():
