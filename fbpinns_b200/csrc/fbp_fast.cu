@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Tiled kernel family: plan matching, launch glue and the deterministic partial-gradient reduction.
 #include "fbp_tc_bwd.cuh"
 
@@ -109,7 +110,10 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
         a.cache = const_cast<float*>(d_cache);
         a.order = tv->d_item_order_bwd;
         if (plan->use_tc_bwd()) {
-            a.cache = nullptr;
+            // no activation cache on this path; the pointer doubles as the trace buffer of the phase-timing experiment
+            // (FBP_TC_DEBUG & 64, tests/tools/bwd_phase_trace.py)
+            const char* dbg_env = getenv("FBP_TC_DEBUG");
+            if (!(dbg_env && (atoi(dbg_env) & 64))) a.cache = nullptr;
             if (int rc = fbp_tc_backward_launch(plan->fast, a, tv->n_items_active, stream)) return rc;
         } else if (int rc = dispatch(plan, true, a, tv->n_items_active, stream)) return rc;
     }

@@ -235,10 +235,24 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         load_idx(0);
         load_val(0);
 
+        // Phase trace (builds with -DFBP_B2_TRACE only: the three extra live registers cost the product kernel 14 %; run with
+        // FBP_TC_DEBUG=64, tests/tools/bwd_phase_trace.py): thread 0 of block 0 records the cycle counter at the phase boundaries
+        // of every tile into the buffer passed as activation cache: [tile][8] = start, a1 arrive, m1 done, a3 arrive, ring
+        // done, m3 done, E2 done, end; [512 + tile * 4 ...] = inside the ring store
+#ifdef FBP_B2_TRACE
+        const bool rec = (dbg & 64) && a.cache != nullptr && blockIdx.x == 0 && tid == 0;
+        const long long rec0 = clock64();
+        auto stamp = [&](int t, int k) { if (rec) a.cache[t * 8 + k] = (float)(clock64() - rec0); };
+        auto stamp_ring = [&](int t, int k) { if (rec) a.cache[512 + t * 4 + k] = (float)(clock64() - rec0); };
+#else
+        auto stamp = [&](int, int) {};
+        auto stamp_ring = [&](int, int) {};
+#endif
         for (int t = 0; t < ntiles; ++t) {
             const int t0 = t * TP;
             const int cnt = min(TP, count - t0);
             const uint32_t par = (uint32_t)(t & 1);
+            stamp(t, 0);
 
             // ---- S0: coordinates, window jets, cotangent of the output-layer jets ----------------------
             float z[3];
@@ -318,6 +332,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&bar_a1);                              // A of MMA 1 written; D3 of the previous tile read
+            stamp(t, 1);
             load_val(t0 + TP);
             // the previous tile's G block (complete before MMA 1 of this tile even starts: the tensor pipe runs in issue
             // order) is added into registers while MMA 1 runs; this tile's G is issued after MMA 3, i.e. after every
@@ -327,6 +342,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
             // ---- E1: a2 -> h2, output-layer gradient partials, tanh transpose -> abar2 -> A operands of MMA 3 ---------
             mbar_wait_or_trap(&bar_m1, par);                   // all of MMA 1: a2 is final and its A operands may be overwritten
             tc_fence_after();
+            stamp(t, 2);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int jb = j0 + 8 * ch;
@@ -368,6 +384,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&bar_a3);
+            stamp(t, 3);
 
             // hi/lo images of abar2 and (t, g, t g) of this thread's point and units -> ring slot of the quarter tile.
             // abar2 is read back from the hi columns of MMA 3's A operands (they hold the unsplit values) instead of
@@ -375,6 +392,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
             auto ring_store = [&]() {
                 const uint32_t use = 2u * (uint32_t)t + (uint32_t)(q >> 1);
                 if (use > 0) mbar_wait_or_trap(&bar_free[slot], (use - 1) & 1);
+                stamp_ring(t, 0);
                 auto put = [&](int img, int e, float x) {
                     ring[img * GK_IMG + (e >> 3) * (int)(GK_SBO / 4) + (e & 7) * 4] = x;
                 };
@@ -385,6 +403,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
 #pragma unroll
                     for (int c = 0; c < C; ++c) tmem_ld8(tbase + lane_base + c * 32 + j0 + 8 * ch, v[c]);
                     tmem_wait_ld();
+                    stamp_ring(t, 1);
 #pragma unroll
                     for (int e8 = 0; e8 < 8; ++e8) {
                         const int e = 8 * ch + e8;
@@ -415,14 +434,18 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
                         }
                     }
                 }
+                stamp_ring(t, 2);
                 fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
                 mbar_arrive(&bar_full[slot]);
+                stamp_ring(t, 3);
             };
             if (q < 2 && !(dbg & 1)) ring_store();             // quarters 0, 1 own the slots first; 2, 3 after their E2
+            stamp(t, 4);
 
             // ---- E2: abar0 = g D_t - 2 t g D_g + g (1 - 3 t^2) D_tg  -> first-layer gradient partials ------------------
             mbar_wait_or_trap(&bar_m3, par);                   // all of MMA 3: its A operands may be rewritten by the next tile
             tc_fence_after();
+            stamp(t, 5);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int kb = j0 + 8 * ch;
@@ -446,7 +469,9 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
                 }
                 l0acc[ch] += (dbg & 32) ? qv[0] + qv[9] + qv[18] + qv[27] : warp_transpose_reduce32(qv, lane);
             }
+            stamp(t, 6);
             if (q >= 2 && !(dbg & 1)) ring_store();
+            stamp(t, 7);
         }
         // ---- end of item: every partial to shared memory.  The last G MMA has completed (so has every ring store). ------
         if (ntiles > 0 && !(dbg & 1)) gather_g((uint32_t)((ntiles - 1) & 1));     // also: every ring read has completed
