@@ -46,7 +46,8 @@ class TakesView(C.Structure):
                 ("d_spair_sub", C.c_void_p), ("d_pos", C.c_void_p), ("d_row_off", C.c_void_p),
                 ("d_pt_row_off", C.c_void_p), ("d_items", C.c_void_p), ("d_sub_item_off", C.c_void_p),
                 ("d_item_order_fwd", C.c_void_p), ("d_item_order_bwd", C.c_void_p),
-                ("n_items", C.c_int32), ("n_items_active", C.c_int32)]
+                ("n_items", C.c_int32), ("n_items_active", C.c_int32),
+                ("d_launch_fwd", C.c_void_p), ("d_launch_bwd", C.c_void_p)]
 
 
 _P = C.c_void_p

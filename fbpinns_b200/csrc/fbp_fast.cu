@@ -60,7 +60,7 @@ static void fill_args(const fbp_plan* plan, const fbp_takes_view* tv, const floa
                       const float* d_sub_static, FastArgs& a) {
     a.x = d_x; a.params = d_params; a.sub_static = d_sub_static;
     a.sub_ids = tv->d_sub_ids; a.spair_point = tv->d_spair_point; a.spair_row = tv->d_spair_row; a.items = tv->d_items;
-    a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr; a.cache = nullptr; a.order = nullptr;
+    a.pair_out = nullptr; a.grow = nullptr; a.gpart = nullptr; a.cache = nullptr; a.order = nullptr; a.launch = nullptr;
     a.xd = plan->dev.xd; a.P = plan->dev.P; a.dbg = 0;
     for (int i = 0; i < FBP_MAX_XD; ++i) a.axis[i] = plan->fast.axis[i];
     for (int i = 0; i < FBP_MAX_COMP; ++i) a.ext[i] = plan->fast.ext[i];
@@ -86,6 +86,7 @@ int fbp_fast_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float
     a.pair_out = d_pair_out;
     a.cache = d_cache;
     a.order = tv->d_item_order_fwd;
+    a.launch = tv->d_launch_fwd;
     if (plan->use_tc()) return fbp_tc_forward_launch(plan->fast, a, tv->n_items, stream);
     return dispatch(plan, false, a, tv->n_items, stream);
 }
@@ -109,6 +110,7 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
         a.gpart = d_gpart;
         a.cache = const_cast<float*>(d_cache);
         a.order = tv->d_item_order_bwd;
+        a.launch = tv->d_launch_bwd;
         if (plan->use_tc_bwd()) {
             // no activation cache on this path; the pointer doubles as the trace buffer of the phase-timing experiment
             // (FBP_TC_DEBUG & 64, tests/tools/bwd_phase_trace.py)

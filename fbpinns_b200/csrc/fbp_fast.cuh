@@ -45,6 +45,7 @@ struct FastArgs {
     const int32_t* spair_row;
     const int32_t* items;
     const int32_t* order;   // optional launch order: block b works on item order[b] (longest first)
+    const int32_t* launch;  // optional [grid][4] launch records (first pair, pair count, subdomain index, item) in launch order
     float* pair_out;     // forward output  [s][C]
     const float* grow;   // reverse input   [q][C]
     float* gpart;        // reverse output  [n_items_active][P]

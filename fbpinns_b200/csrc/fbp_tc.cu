@@ -292,3 +292,10 @@ int fbp_tc_backward_launch(const FastSpec& f, const FastArgs& a, int grid, cudaS
     fbp_set_error("fbp_tc: no tensor-family reverse instance for jets=(%d,%d)", f.na2, f.na1);
     return 3;
 }
+
+#ifdef FBP_BLOCK_TRACE
+// trace builds only (tests/tools/item_cost_trace.py): the buffer the CTAs of the tensor kernels record their timeline into
+extern "C" int fbp_debug_set_block_trace(void* d_buf) {
+    return cudaMemcpyToSymbol(fbptc::fbp_blk_trace, &d_buf, sizeof(void*)) == cudaSuccess ? 0 : 1;
+}
+#endif

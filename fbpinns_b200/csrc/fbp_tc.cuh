@@ -31,6 +31,39 @@
 
 namespace fbptc {
 
+// Per-CTA timeline of the tensor kernels (builds with -DFBP_BLOCK_TRACE only, tests/tools/item_cost_trace.py): thread 0 of every
+// CTA records [8 * block + k] = 0 SM id, 1 entry, 2 prologue done, 3 its tile loop done, 4 every warp done, 5 exit (low 32 bits of
+// the SM's cycle counter), 6 tiles, 7 exit on the global nanosecond timer.  Nothing of it exists in the product build.
+#ifdef FBP_BLOCK_TRACE
+__device__ uint32_t* fbp_blk_trace = nullptr;
+__device__ __forceinline__ void blk_stamp(int k) {
+#ifdef FBP_BLK_MASK
+    if (!((FBP_BLK_MASK >> k) & 1)) return;
+#endif
+    if (threadIdx.x == 0 && fbp_blk_trace) fbp_blk_trace[8 * blockIdx.x + k] = (uint32_t)clock64();
+}
+__device__ __forceinline__ void blk_stamp_entry(int ntiles) {
+    if (threadIdx.x == 0 && fbp_blk_trace) {
+        uint32_t smid;
+        uint64_t ns;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        fbp_blk_trace[8 * blockIdx.x + 0] = smid;
+        fbp_blk_trace[8 * blockIdx.x + 6] = (uint32_t)ntiles;
+        fbp_blk_trace[8 * blockIdx.x + 7] = (uint32_t)ns;
+    }
+}
+#ifdef FBP_BLOCK_TRACE3
+#define BLK_STAMP3 blk_stamp(3)
+#else
+#define BLK_STAMP3
+#endif
+#else
+#define BLK_STAMP3
+__device__ __forceinline__ void blk_stamp(int) {}
+__device__ __forceinline__ void blk_stamp_entry(int) {}
+#endif
+
 constexpr int TP = 128;           // pairs per tile = TMEM lanes
 constexpr int NT = 256;           // threads: 2 warpgroups x 128 point rows
 constexpr int H = 32;
@@ -501,6 +534,89 @@ __global__ void __launch_bounds__(128 * NWG, 1) tc_forward_kernel(FastArgs a) {
 
 
 // =====================================================================================================
+// prologue of the second-generation kernels
+// =====================================================================================================
+// A work item costs a fixed ~10 000 cycles before its first tile when the launch order, the work list, the subdomain index
+// and the parameters are four dependent global loads and the staging passes are separated by CTA barriers
+// (profiles/r2h_item_cost.md).  Here: one 16-byte launch record (fbp_takes_view.d_launch_*), tensor-memory allocation and
+// barrier initialisation issued before the loads, every parameter read straight from global memory (kappa_s recomputed per
+// element instead of read back from shared memory), bank-conflict-free placement of the B operands, ONE barrier.
+struct ItemRec { int first, count, im, item; };
+__device__ __forceinline__ ItemRec tc_item(const FastArgs& a) {
+    ItemRec r;
+    if (a.launch != nullptr) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(a.launch) + blockIdx.x);
+        r.first = v.x; r.count = v.y; r.im = v.z; r.item = v.w;
+    } else {
+        r.item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
+        r.first = a.items[r.item * 4 + 1];
+        r.count = a.items[r.item * 4 + 2];
+        r.im = a.sub_ids[a.items[r.item * 4 + 0]];
+    }
+    return r;
+}
+
+// the small parameter vectors (first layer, biases, output weights) into the CF::SM_* block; no barrier inside
+template <class CF>
+__device__ __forceinline__ void tc_stage_small(float* sm, const float* __restrict__ prow, int xd, const float (&isd)[3],
+                                               const int (&axis)[FBP_MAX_XD], int tid, int nt) {
+    for (int i = tid; i < 3 * H; i += nt) {
+        const int d = i >> 5, j = i & 31;
+        sm[CF::SM_W0 + i] = d < xd ? prow[j * xd + d] : 0.0f;
+    }
+    for (int i = tid; i < H; i += nt) sm[CF::SM_B0 + i] = prow[H * xd + i];
+    for (int i = tid; i < CF::NS * H; i += nt) {
+        const int s_ = i >> 5, j = i & 31, ax = axis[s_];
+        sm[CF::SM_W0D + i] = prow[j * xd + ax] * sel3(ax, isd[0], isd[1], isd[2]);
+    }
+    const int off = H * xd + H + H * H;
+    for (int i = tid; i < H; i += nt) {
+        sm[CF::SM_B1 + i] = prow[off + i];
+        sm[CF::SM_WL + i] = prow[off + H + i];
+    }
+    if (tid == 0) sm[CF::SM_BL] = prow[off + 2 * H];
+}
+
+// B operands, hi / lo, canonical K-major layout:  b1[v][n = j][k] = W1[j][k] sc1_v[k]  (sc1 = 1, -2 kappa_s^2),  and, for the
+// reverse kernel,  b2[v][n = k][j] = W1[j][k] sc2_v[k]  (sc2 = 1, kappa_s, -2 kappa_s^2).  Lane -> (j, k) is chosen so that the
+// 32 stores of a warp hit 32 (b1) / 16 (b2) different banks.
+template <class CF, bool WITH_B2>
+__device__ __forceinline__ void tc_stage_b(float* b1, float* b2, const float* __restrict__ prow, int xd, const float (&isd)[3],
+                                           const int (&axis)[FBP_MAX_XD], int tid, int nt) {
+    constexpr int NS = CF::NS, NA2 = CF::NA2, NB1 = 1 + NA2, NB2 = 1 + NS + NA2, HH = H * H;
+    const float* w1 = prow + H * xd + H;
+    for (int i = tid; i < HH; i += nt) {
+        const int ln = i & 31, grp = i >> 5;
+        const int j = ((grp & 3) << 3) | (((ln >> 4) & 1) << 2) | (ln & 3);
+        const int k = ((grp >> 2) << 2) | ((ln >> 2) & 3);
+        const float w = w1[j * H + k];
+        float kap[NS > 0 ? NS : 1];
+#pragma unroll
+        for (int s_ = 0; s_ < NS; ++s_) kap[s_] = prow[k * xd + axis[s_]] * sel3(axis[s_], isd[0], isd[1], isd[2]);
+#pragma unroll
+        for (int v = 0; v < NB1; ++v) {
+            const float sc = v == 0 ? 1.0f : -2.0f * kap[v > 0 ? v - 1 : 0] * kap[v > 0 ? v - 1 : 0];
+            uint32_t hi, lo;
+            tf32_split(w * sc, hi, lo);
+            b1[(2 * v) * HH + bcore_index(j, k)] = __uint_as_float(hi);
+            b1[(2 * v + 1) * HH + bcore_index(j, k)] = __uint_as_float(lo);
+        }
+        if (WITH_B2) {
+#pragma unroll
+            for (int v = 0; v < NB2; ++v) {
+                float sc = 1.0f;
+                if (v >= 1 && v <= NS) sc = kap[v >= 1 && v <= NS ? v - 1 : 0];
+                else if (v > NS) sc = -2.0f * kap[v > NS ? v - 1 - NS : 0] * kap[v > NS ? v - 1 - NS : 0];
+                uint32_t hi, lo;
+                tf32_split(w * sc, hi, lo);
+                b2[(2 * v) * HH + bcore_index(k, j)] = __uint_as_float(hi);
+                b2[(2 * v + 1) * HH + bcore_index(k, j)] = __uint_as_float(lo);
+            }
+        }
+    }
+}
+
+// =====================================================================================================
 // forward, software-pipelined kernel (the default: FBP_TC_FWD=2)
 // =====================================================================================================
 // The first kernel pays the tensor-core time and ~0.85 ms of latency serially because only one tile fits tensor memory
@@ -538,13 +654,19 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     float* outN = sm + L::OFF_OUT;
 
     const int tid = threadIdx.x, warp = warp_uniform();
+    blk_stamp(1);
     const int g = (tid >> 7) & 3, r = tid & 127;
     const int jb = 8 * g;                   // this thread's 8 hidden units
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
-    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
-    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
-    const int im = a.sub_ids[sp];
+    const ItemRec it = tc_item(a);
+    const int first = it.first, count = it.count, im = it.im;
+    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);          // its latency hides under the parameter loads
+    if (tid == 32) {
+        mbar_init(&bar_a, F2_NPT);          // every epilogue thread: A(t+1) written and D(t) held in registers
+        mbar_init(&bar_m, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int xd = a.xd;
     const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
     float mu[3], isd[3];
@@ -558,17 +680,9 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     }
     const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
     const float* prow = a.params + (int64_t)im * a.P;
-    fast_load_params<CF, F2_NT>(sm, prow, xd, isd, a.axis, false);
-    __syncthreads();
-    stage_b1_variants<CF>(sm + L::OFF_B1, prow + H * xd + H, sm, tid, F2_NT);
-    if (tid == 0) {
-        mbar_init(&bar_a, F2_NPT);          // every epilogue thread: A(t+1) written and D(t) held in registers
-        mbar_init(&bar_m, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    tc_stage_small<CF>(sm, prow, xd, isd, a.axis, tid, F2_NT);
+    tc_stage_b<CF, false>(sm + L::OFF_B1, nullptr, prow, xd, isd, a.axis, tid, F2_NT);
     fence_proxy_async();
-    __syncthreads();
-    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -596,6 +710,7 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
             __syncwarp();
         }
     } else if (warp < 16) {
+        blk_stamp(2);
         int pf_pt = 0;
         float pf_x[3] = {0.0f, 0.0f, 0.0f};
         auto load_idx = [&](int tt) {
@@ -756,10 +871,14 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) z_cur[d] = z_next[d];
         }
+        BLK_STAMP3;
     }
     tc_fence_before();
     __syncthreads();
+    blk_stamp(4);
     if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);
+    blk_stamp(5);
+    blk_stamp_entry(ntiles);
 }
 
 }  // namespace fbptc

@@ -91,83 +91,59 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t bar_a1, bar_a3, bar_m1, bar_m3, bar_full[2], bar_free[2], bar_gtile;
     __shared__ uint32_t tmem_slot;
+    __shared__ int hdr_i[4];                  // first pair, pair count, subdomain index, item
+    __shared__ float hdr_f[8];                // mu[3], 1/sd[3], window flag, output scale
 
     const int tid = threadIdx.x, warp = warp_uniform(), lane = tid & 31;
+    blk_stamp(1);
     // a.dbg (timing experiments only, results are then wrong): 1 = no weight-gradient staging / G MMAs, 4 = no ring stores
     // (the G MMAs run on stale images), 8 = no G MMA issue (the stores happen), 32 = no butterfly
     const int dbg = a.dbg;
 
-    const int item = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
-    const int sp = a.items[item * 4 + 0], first = a.items[item * 4 + 1], count = a.items[item * 4 + 2];
-    const int im = a.sub_ids[sp];
     const int xd = a.xd;
-    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
-    float mu[3], isd[3];
+    {   // prologue: nothing computed here stays in registers (the header in shared memory is re-read per role below, so that
+        // the register allocation of the tile loop does not depend on this block)
+        const ItemRec it = tc_item(a);
+        if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);          // its latency hides under the parameter loads
+        const float* ss = a.sub_static + (int64_t)it.im * (2 * xd + 3);
+        float isd_[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        if (d < xd) {
-            const float lo = ss[d], hi = ss[xd + d];
-            mu[d] = (hi + lo) * 0.5f;
-            isd[d] = 1.0f / ((hi - lo) * 0.5f);
-        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
-    }
-    const float flag = ss[2 * xd], un_sd = ss[2 * xd + 2];
-    const float* prow = a.params + (int64_t)im * a.P;
-    fast_load_params<CF, B2_NT>(sm, prow, xd, isd, a.axis, false);
-    __syncthreads();
-    {   // B operands: W1 and its scaled variants, hi/lo, canonical K-major layout
-        const float* w1 = prow + H * xd + H;
-        for (int i = tid; i < HH; i += B2_NT) {
-            const int j = i >> 5, k = i & 31;
-            const float w = w1[i];
-            float sc1[L::NB1], sc2[L::NB2];
-            sc1[0] = 1.0f;
-            sc2[0] = 1.0f;
+        for (int d = 0; d < 3; ++d) isd_[d] = d < xd ? 1.0f / ((ss[xd + d] - ss[d]) * 0.5f) : 0.0f;
+        if (tid == 32) {
+            hdr_i[0] = it.first; hdr_i[1] = it.count; hdr_i[2] = it.im; hdr_i[3] = it.item;
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const float kap = sm[CF::SM_W0D + s * H + k];
-                sc2[1 + s] = kap;
-                if (s < NA2) {
-                    sc1[1 + s] = -2.0f * kap * kap;
-                    sc2[1 + NS + s] = -2.0f * kap * kap;
-                }
+            for (int d = 0; d < 3; ++d) {
+                hdr_f[d] = d < xd ? (ss[xd + d] + ss[d]) * 0.5f : 0.0f;
+                hdr_f[3 + d] = isd_[d];
             }
+            hdr_f[6] = ss[2 * xd];
+            hdr_f[7] = ss[2 * xd + 2];
+            mbar_init(&bar_a1, B2_NPT);
+            mbar_init(&bar_a3, B2_NPT);
+            mbar_init(&bar_gtile, 1);
+            mbar_init(&bar_m1, 1);
+            mbar_init(&bar_m3, 1);
 #pragma unroll
-            for (int v = 0; v < L::NB1; ++v) {
-                uint32_t hi, lo;
-                tf32_split(w * sc1[v], hi, lo);
-                sm[L::OFF_B1 + (2 * v) * HH + bcore_index(j, k)] = __uint_as_float(hi);
-                sm[L::OFF_B1 + (2 * v + 1) * HH + bcore_index(j, k)] = __uint_as_float(lo);
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_full[i], 32 * NG);   // the NG warps of a quarter tile
+                mbar_init(&bar_free[i], 1);
             }
-#pragma unroll
-            for (int v = 0; v < L::NB2; ++v) {
-                uint32_t hi, lo;
-                tf32_split(w * sc2[v], hi, lo);
-                sm[L::OFF_B2 + (2 * v) * HH + bcore_index(k, j)] = __uint_as_float(hi);
-                sm[L::OFF_B2 + (2 * v + 1) * HH + bcore_index(k, j)] = __uint_as_float(lo);
-            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-    }
-    if (tid == 0) {
-        mbar_init(&bar_a1, B2_NPT);
-        mbar_init(&bar_a3, B2_NPT);
-        mbar_init(&bar_gtile, 1);
-        mbar_init(&bar_m1, 1);
-        mbar_init(&bar_m3, 1);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_full[i], 32 * NG);   // the NG warps of a quarter tile
-            mbar_init(&bar_free[i], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const float* prow = a.params + (int64_t)it.im * a.P;
+        tc_stage_small<CF>(sm, prow, xd, isd_, a.axis, tid, B2_NT);
+        tc_stage_b<CF, true>(sm + L::OFF_B1, sm + L::OFF_B2, prow, xd, isd_, a.axis, tid, B2_NT);
     }
     fence_proxy_async();
-    __syncthreads();
-    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_slot;
+    const int first = hdr_i[0], count = hdr_i[1];
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { mu[d] = hdr_f[d]; isd[d] = hdr_f[3 + d]; }
+    const float flag = hdr_f[6], un_sd = hdr_f[7];
     const int ntiles = (count + TP - 1) / TP;
     // registers move from the MMA warpgroup to the point warpgroups (what the former frees is what the latter take)
     if (NG == 2) {
@@ -184,6 +160,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         // =============================================================================================
         // point warps
         // =============================================================================================
+        blk_stamp(2);
         const int g = warp >> 2, q = warp & 3;
         const int r = tid & 127;                    // point row of the tile = TMEM lane
         const int j0 = UPT * g;
@@ -473,6 +450,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
             if (q >= 2 && !(dbg & 1)) ring_store();
             stamp(t, 7);
         }
+        BLK_STAMP3;
         // ---- end of item: every partial to shared memory.  The last G MMA has completed (so has every ring store). ------
         if (ntiles > 0 && !(dbg & 1)) gather_g((uint32_t)((ntiles - 1) & 1));     // also: every ring read has completed
 #pragma unroll
@@ -570,6 +548,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
     }
 
     __syncthreads();
+    blk_stamp(4);
 
     const float* gd = red + L::RED_GD;
     // G_g[s][j][k], G_tg[s][j][k], G_t[j][k]: the hi and lo rows of the stacks added
@@ -577,6 +556,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
     auto Gtg = [&](int s, int j, int k) { return gd[(32 * s + j) * 96 + 32 + k] + gd[(64 + 32 * s + j) * 96 + 32 + k]; };
     auto Gt = [&](int j, int k) { return gd[j * 96 + 64 + k] + gd[(32 + j) * 96 + 64 + k]; };
     // derivative path of the first layer: kappa_bar_s[k] = sum_j W1[j][k] (G_g[s][j][k] - 4 kappa_s[k] G_tg[s][j][k])
+    const float* w1g = a.params + (int64_t)hdr_i[2] * a.P + H * xd + H;      // W1[j][k], L2-resident since the prologue
     for (int i = tid; i < NS * H; i += B2_NT) {
         const int s = i >> 5, k = i & 31;
         const float kap = sm[CF::SM_W0D + s * H + k];
@@ -584,13 +564,13 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         for (int j = 0; j < H; ++j) {
             float gsum = Gg(s, j, k);
             if (s < NA2) gsum = fmaf(-4.0f * kap, Gtg(s, j, k), gsum);
-            v = fmaf(sm[CF::SM_WT1 + k * H + j], gsum, v);
+            v = fmaf(w1g[j * H + k], gsum, v);
         }
         red[L::RED_KB + i] = v;
     }
     __syncthreads();
 
-    float* gp = a.gpart + (int64_t)item * a.P;
+    float* gp = a.gpart + (int64_t)hdr_i[3] * a.P;
     // first layer, value path: (unit k, quantity t) sits in lane (k % 8) * 4 + t of chunk (k % UPT) / 8 of the four point warps
     // of unit group k / UPT
     auto l0 = [&](int k, int t) {
@@ -605,7 +585,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         float v = l0(j, 1 + d);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
-            if (a.axis[s] == d) v = fmaf(sel3(d, isd[0], isd[1], isd[2]), red[L::RED_KB + s * H + j], v);
+            if (a.axis[s] == d) v = fmaf(hdr_f[3 + d], red[L::RED_KB + s * H + j], v);
         gp[i] = v;
     }
     for (int i = tid; i < H; i += B2_NT) gp[H * xd + i] = l0(i, 0);
@@ -639,6 +619,8 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);
+    blk_stamp(5);
+    blk_stamp_entry(ntiles);
 }
 
 }  // namespace fbptc

@@ -272,7 +272,8 @@ class DeviceTakes:
         dev = decomp.device
         self.n = int(x.shape[0])
         self.m_all, self.m_active, self.npou = int(len(all_ims)), int(m_active), decomp.npou
-        self.sub_ids = torch.as_tensor(np.asarray(all_ims, dtype=np.int32), dtype=I32, device=dev)
+        self.sub_ids_host = np.asarray(all_ims, dtype=np.int32)
+        self.sub_ids = torch.as_tensor(self.sub_ids_host, dtype=I32, device=dev)
         pos_d = torch.as_tensor(np.asarray(pos_of_model, dtype=np.int32), dtype=I32, device=dev)
         b = C.c_void_p()
         s, q = C.c_int64(), C.c_int64()
@@ -312,6 +313,15 @@ class DeviceTakes:
         self.item_order_fwd = torch.as_tensor(order_fwd, dtype=I32, device=dev)
         self.item_order_bwd = torch.as_tensor(order_bwd, dtype=I32, device=dev)
         self.n_items, self.n_items_active = int(items.shape[0]), nia
+        # launch records of the tensor kernels: what block b needs, in one 16-byte load (first pair, pair count, global
+        # subdomain index, item) instead of order -> items -> sub_ids (include/fbpinn_b200.h d_launch_*)
+        ims = np.asarray(self.sub_ids_host, dtype=np.int32)
+
+        def launch(order):
+            it = items[order]
+            return np.stack([it[:, 1], it[:, 2], ims[it[:, 0]], order.astype(np.int32)], axis=1).astype(np.int32).reshape(-1)
+        self.launch_fwd = torch.as_tensor(launch(order_fwd), dtype=I32, device=dev)
+        self.launch_bwd = torch.as_tensor(launch(order_bwd), dtype=I32, device=dev)
         self.tile_points = tile_points
         self._view = None
 
@@ -325,7 +335,8 @@ class DeviceTakes:
                             ("d_spair_row", self.spair_row), ("d_spair_sub", self.spair_sub), ("d_pos", self.pos),
                             ("d_row_off", self.row_off), ("d_pt_row_off", self.pt_row_off), ("d_items", self.items),
                             ("d_sub_item_off", self.sub_item_off), ("d_item_order_fwd", self.item_order_fwd),
-                            ("d_item_order_bwd", self.item_order_bwd)]:
+                            ("d_item_order_bwd", self.item_order_bwd), ("d_launch_fwd", self.launch_fwd),
+                            ("d_launch_bwd", self.launch_bwd)]:
                 setattr(v, name, t.data_ptr() if t.numel() else None)
             v.n_items, v.n_items_active = self.n_items, self.n_items_active
             self._view = v

@@ -105,6 +105,11 @@ typedef struct fbp_takes_view {
     const int32_t* d_item_order_bwd; /* [n_items_active] launch order of the active items, NULL = identity */
     int32_t n_items;             /* built by the host from d_sub_off (fbp_plan_tile_points) */
     int32_t n_items_active;      /* leading items that belong to active subdomains */
+    /* optional (NULL = resolved on the device through d_item_order_*, d_items, d_sub_ids: two more dependent loads per
+       work item): the same information flattened into one 16-byte record per launched block, in launch order:
+       (first pair, pair count, global subdomain index, item) */
+    const int32_t* d_launch_fwd; /* [n_items][4] */
+    const int32_t* d_launch_bwd; /* [n_items_active][4] */
 } fbp_takes_view;
 
 /* ---- errors / info ---------------------------------------------------------------------------- */
