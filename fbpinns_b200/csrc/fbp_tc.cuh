@@ -82,6 +82,9 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, 
     // base offset [49,52) = 0, lbo mode [52] = 0, layout type [61,64) = 0 (SWIZZLE_NONE)
     return d;
 }
+// descriptor of the same layout `bytes` further on (bytes % 16 == 0, same 256 KB window): ONE 64-bit add of a constant on the
+// uniform datapath, where make_smem_desc of the new address costs the issuing warp ~6 dependent instructions per MMA
+__host__ __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
 // instruction descriptor of tcgen05.mma.kind::tf32, FP32 accumulate; a_mn / b_mn = 1: the operand is MN-major (the
 // MN-major form failed its hardware self-test in round 2 and is not used; every operand of the family is K-major)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn = 0, int b_mn = 0) {
@@ -650,6 +653,10 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t bar_a, bar_m;
     __shared__ uint32_t tmem_slot;
+#ifdef FBP_F2_HDR
+    __shared__ int hdr_i[2];
+    __shared__ float hdr_f[9];
+#endif
     float* exch = sm + L::OFF_EXCH;
     float* outN = sm + L::OFF_OUT;
 
@@ -659,6 +666,44 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     const int jb = 8 * g;                   // this thread's 8 hidden units
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
+#ifdef FBP_F2_HDR
+    const int xd = a.xd;
+    {   // prologue: nothing computed here stays in registers (see tc_backward_kernel2)
+        const ItemRec it = tc_item(a);
+        if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+        const float* ss = a.sub_static + (int64_t)it.im * (2 * xd + 3);
+        float isd_[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) isd_[d] = d < xd ? 1.0f / ((ss[xd + d] - ss[d]) * 0.5f) : 0.0f;
+        if (tid == 32) {
+            hdr_i[0] = it.first; hdr_i[1] = it.count;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                hdr_f[d] = d < xd ? (ss[xd + d] + ss[d]) * 0.5f : 0.0f;
+                hdr_f[3 + d] = isd_[d];
+            }
+            hdr_f[6] = ss[2 * xd];
+            hdr_f[7] = ss[2 * xd + 1];
+            hdr_f[8] = ss[2 * xd + 2];
+            mbar_init(&bar_a, F2_NPT);
+            mbar_init(&bar_m, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        const float* prow = a.params + (int64_t)it.im * a.P;
+        tc_stage_small<CF>(sm, prow, xd, isd_, a.axis, tid, F2_NT);
+        tc_stage_b<CF, false>(sm + L::OFF_B1, nullptr, prow, xd, isd_, a.axis, tid, F2_NT);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_slot;
+    const int first = hdr_i[0], count = hdr_i[1];
+    float mu[3], isd[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { mu[d] = hdr_f[d]; isd[d] = hdr_f[3 + d]; }
+    const float flag = hdr_f[6], un_mu = hdr_f[7], un_sd = hdr_f[8];
+#else
     const ItemRec it = tc_item(a);
     const int first = it.first, count = it.count, im = it.im;
     if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);          // its latency hides under the parameter loads
@@ -687,13 +732,14 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_slot;
+#endif
     const int ntiles = (count + TP - 1) / TP;
     if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
 
     if (warp == 16) {
         // ---- MMA warp: tile t's products as soon as its A operands are complete and the previous D has been read ----
-        const uint32_t b1 = smem_u32(sm + L::OFF_B1);
+        const uint64_t b1base = make_smem_desc(smem_u32(sm + L::OFF_B1), B_LBO, B_SBO);
         for (int t = 0; t < ntiles; ++t) {
             mbar_wait_or_trap(&bar_a, (uint32_t)(t & 1));
             tc_fence_after();
@@ -702,8 +748,8 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
                 for (int c = 0; c < C; ++c) {
                     const int ia = FA::ia(c), vb = FA::vb(c);
                     issue_gemm_acc<32>(tbase + COL_D + c * 32, tbase + ia * 32, tbase + COL_ALO + ia * 32,
-                                       make_smem_desc(b1 + (uint32_t)((2 * vb) * H * H * 4), B_LBO, B_SBO),
-                                       make_smem_desc(b1 + (uint32_t)((2 * vb + 1) * H * H * 4), B_LBO, B_SBO), true);
+                                       desc_advance(b1base, (uint32_t)((2 * vb) * H * H * 4)),
+                                       desc_advance(b1base, (uint32_t)((2 * vb + 1) * H * H * 4)), true);
                 }
                 mma_commit(&bar_m);
             }

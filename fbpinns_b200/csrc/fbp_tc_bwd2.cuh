@@ -70,14 +70,109 @@ struct Bwd2Cfg {
     static constexpr int img_at(int part) { return 8 + part; }                   // value abar2 (the M = 128 MMA also reads 10, 11)
     static constexpr int img_phi(int f, int part) { return 10 + 2 * f + part; }  // f: 0 t, 1 g, 2 t g
     // end-of-item scratch (floats, over the ring)
-    static constexpr int RED_GD = 0;                            // [128 lanes][96]
+#ifndef FBP_B2_GDS
+#define FBP_B2_GDS 100
+#endif
+    static constexpr int GDS = FBP_B2_GDS;                      // row stride of RED_GD: 100 floats = conflict-free 16-byte stores
+    static constexpr int RED_GD = 0;                            // [128 lanes][GDS], 96 used
     static constexpr int RED_L0 = SLOT;                         // [point warps][chunks][32]
     static constexpr int RED_WL = RED_L0 + D::NPW * D::NCH * 32;    // [UPT][point threads]
     static constexpr int RED_B1 = RED_WL + D::UPT * D::NPT;     // [UPT][point threads]
     static constexpr int RED_BL = RED_B1 + D::UPT * D::NPT;     // [point warps]
-    static constexpr int RED_KB = RED_BL + D::NPW;              // [max(NS,1)][32]
-    static_assert(128 * 96 <= SLOT && RED_KB + 2 * 32 <= 2 * SLOT, "reduction scratch must fit the ring");
+    static constexpr int RED_KB = RED_BL + D::NPW;              // [max(NS,1)][8 partial sums over j][32]
+    static_assert(128 * GDS <= SLOT && RED_KB + (NS > 0 ? NS : 1) * 8 * 32 <= 2 * SLOT, "reduction scratch must fit the ring");
 };
+
+// End of a work item: the partial sums the point threads left in shared memory (RED_*) -> this item's row of gpart.  A
+// separate function on purpose: the instruction schedule of the tile loop of tc_backward_kernel2 is sensitive to any code
+// compiled with it (the same loop ran at 14.1 k to 15.7 k cycles per tile across builds that only differed here,
+// profiles/r2h_item_cost.md); w1g = W1[j][k] of the subdomain in global memory (L2-resident since the prologue).
+__device__ __forceinline__ int sel3i(int i, int a, int b, int c) { return i == 0 ? a : (i == 1 ? b : c); }
+#ifdef FBP_B2_FINISH_CALL
+#define B2_FINISH_INLINE __noinline__
+#else
+#define B2_FINISH_INLINE __forceinline__
+#endif
+template <class CF, int NG>
+__device__ B2_FINISH_INLINE void b2_finish(float* sm, const float* __restrict__ w1g, float* __restrict__ gp, int xd, int3 axis, float3 isd) {
+    using L = Bwd2Cfg<CF, NG>;
+    using DM = B2Dim<NG>;
+    constexpr int B2_NPT = DM::NPT, B2_NT = DM::NT, UPT = DM::UPT, NCH = DM::NCH;
+    constexpr int NS = CF::NS, NA2 = CF::NA2, HH = H * H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* red = sm + L::OFF_RING;
+    const float* gd = red + L::RED_GD;
+    constexpr int GDS = L::GDS;
+    // G_g[s][j][k], G_tg[s][j][k], G_t[j][k]: the hi and lo rows of the stacks added
+    auto Gg = [&](int s, int j, int k) { return gd[(32 * s + j) * GDS + k] + gd[(64 + 32 * s + j) * GDS + k]; };
+    auto Gtg = [&](int s, int j, int k) { return gd[(32 * s + j) * GDS + 32 + k] + gd[(64 + 32 * s + j) * GDS + 32 + k]; };
+    auto Gt = [&](int j, int k) { return gd[j * GDS + 64 + k] + gd[(32 + j) * GDS + 64 + k]; };
+    // derivative path of the first layer: kappa_bar_s[k] = sum_j W1[j][k] (G_g[s][j][k] - 4 kappa_s[k] G_tg[s][j][k]);
+    // a warp = (slot s, 4 rows j), lane = k; the 8 partial sums are added by the reader
+    for (int i = tid; i < NS * 8 * H; i += B2_NT) {
+        const int s = i >> 8, part = (i >> 5) & 7, k = i & 31;
+        const float kap = sm[CF::SM_W0D + s * H + k];
+        float v = 0.0f;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * part + jj;
+            float gsum = Gg(s, j, k);
+            if (s < NA2) gsum = fmaf(-4.0f * kap, Gtg(s, j, k), gsum);
+            v = fmaf(w1g[j * H + k], gsum, v);
+        }
+        red[L::RED_KB + i] = v;
+    }
+    __syncthreads();
+
+    // first layer, value path: (unit k, quantity t) sits in lane (k % 8) * 4 + t of chunk (k % UPT) / 8 of the four point warps
+    // of unit group k / UPT
+    auto l0 = [&](int k, int t) {
+        const int gg_ = k / UPT, ch = (k % UPT) >> 3, ln = (k & 7) * 4 + t;
+        float v = 0.0f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) v += red[L::RED_L0 + ((gg_ * 4 + qq) * NCH + ch) * 32 + ln];
+        return v;
+    };
+    for (int i = tid; i < H * xd; i += B2_NT) {
+        const int j = i / xd, d = i - j * xd;
+        float v = l0(j, 1 + d);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (sel3i(s, axis.x, axis.y, axis.z) == d) {
+                float kb = 0.0f;
+#pragma unroll
+                for (int part = 0; part < 8; ++part) kb += red[L::RED_KB + (s * 8 + part) * H + j];
+                v = fmaf(sel3(d, isd.x, isd.y, isd.z), kb, v);
+            }
+        gp[i] = v;
+    }
+    for (int i = tid; i < H; i += B2_NT) gp[H * xd + i] = l0(i, 0);
+    int off = H * xd + H;
+    for (int i = tid; i < HH; i += B2_NT) {
+        const int j = i >> 5, k = i & 31;
+        float v = Gt(j, k);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float kap = sm[CF::SM_W0D + s * H + k];
+            v = fmaf(kap, Gg(s, j, k), v);
+            if (s < NA2) v = fmaf(-2.0f * kap * kap, Gtg(s, j, k), v);
+        }
+        gp[off + i] = v;
+    }
+    off += HH;
+    for (int o = warp; o < 2 * H; o += B2_NT / 32) {   // hidden bias and output weights: sums over the 128 point threads of the unit's group
+        const int j = o & 31;
+        const float* src = red + (o < H ? L::RED_B1 : L::RED_WL) + (j % UPT) * B2_NPT + (j / UPT) * 128;
+        const float v = fbp_warp_sum((src[lane] + src[lane + 32]) + (src[lane + 64] + src[lane + 96]));
+        if (lane == 0) gp[off + o] = v;
+    }
+    off += 2 * H;
+    if (tid == 0) {
+        float v = 0.0f;
+        for (int w = 0; w < 4; ++w) v += red[L::RED_BL + w];    // warps 0-3 are unit half 0 (the only ones that count it)
+        gp[off] = v;
+    }
+}
 
 template <class CF, int NG>
 __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs a) {
@@ -454,7 +549,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         // ---- end of item: every partial to shared memory.  The last G MMA has completed (so has every ring store). ------
         if (ntiles > 0 && !(dbg & 1)) gather_g((uint32_t)((ntiles - 1) & 1));     // also: every ring read has completed
 #pragma unroll
-        for (int u = 0; u < GCOLS; ++u) red[L::RED_GD + (q * 32 + lane) * 96 + GCOLS * g + u] = gacc[u];
+        for (int u = 0; u < GCOLS; ++u) red[L::RED_GD + (q * 32 + lane) * L::GDS + GCOLS * g + u] = gacc[u];
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch) red[L::RED_L0 + (warp * NCH + ch) * 32 + lane] = l0acc[ch];
 #pragma unroll
@@ -468,10 +563,12 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         // =============================================================================================
         // MMA warp
         // =============================================================================================
-        const uint32_t b1 = smem_u32(sm + L::OFF_B1), b2 = smem_u32(sm + L::OFF_B2);
-        auto b1d = [&](int v, int part) { return make_smem_desc(b1 + (uint32_t)((2 * v + part) * HH * 4), B_LBO, B_SBO); };
-        auto b2d = [&](int v, int part) { return make_smem_desc(b2 + (uint32_t)((2 * v + part) * HH * 4), B_LBO, B_SBO); };
-        const uint32_t ring0 = smem_u32(sm + L::OFF_RING);
+        // three base descriptors; every operand descriptor of the tile loop is one of them plus a compile-time constant
+        const uint64_t b1base = make_smem_desc(smem_u32(sm + L::OFF_B1), B_LBO, B_SBO);
+        const uint64_t b2base = make_smem_desc(smem_u32(sm + L::OFF_B2), B_LBO, B_SBO);
+        const uint64_t gbase = make_smem_desc(smem_u32(sm + L::OFF_RING), GK_LBO, GK_SBO);
+        auto b1d = [&](int v, int part) { return desc_advance(b1base, (uint32_t)((2 * v + part) * HH * 4)); };
+        auto b2d = [&](int v, int part) { return desc_advance(b2base, (uint32_t)((2 * v + part) * HH * 4)); };
         constexpr uint32_t idesc_g = make_idesc_tf32(128, 32);
         for (int t = 0; t < ntiles; ++t) {
             const uint32_t par = (uint32_t)(t & 1);
@@ -518,17 +615,17 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
                 const int slot = qi & 1;
                 mbar_wait_or_trap(&bar_full[slot], (uint32_t)(qi >> 1));
                 if (elect_one()) {
-                    const uint32_t rbase = ring0 + (uint32_t)(slot * L::SLOT * 4);
+                    const uint64_t gslot = slot ? desc_advance(gbase, (uint32_t)(L::SLOT * 4)) : gbase;
                     const bool fresh = (qi == 0);                 // every tile starts fresh accumulators
                     auto block = [&](int a_img, int b_img, uint32_t dcol) {
-                        const uint64_t ad = make_smem_desc(rbase + (uint32_t)(a_img * GK_IMG * 4), GK_LBO, GK_SBO);
 #pragma unroll
                         for (int part = 0; part < 2; ++part) {
-                            const uint64_t bd = make_smem_desc(rbase + (uint32_t)((b_img + part) * GK_IMG * 4), GK_LBO, GK_SBO);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t adv = (uint64_t)((ks * 2 * GK_LBO) >> 4);
-                                mma_tf32_ss(tbase + dcol, ad + adv, bd + adv, idesc_g, (fresh && part == 0 && ks == 0) ? 0u : 1u);
+                                const uint32_t adv = (uint32_t)(ks * 2 * GK_LBO);
+                                mma_tf32_ss(tbase + dcol, desc_advance(gslot, (uint32_t)(a_img * GK_IMG * 4) + adv),
+                                            desc_advance(gslot, (uint32_t)((b_img + part) * GK_IMG * 4) + adv), idesc_g,
+                                            (fresh && part == 0 && ks == 0) ? 0u : 1u);
                             }
                         }
                     };
@@ -550,72 +647,8 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
     __syncthreads();
     blk_stamp(4);
 
-    const float* gd = red + L::RED_GD;
-    // G_g[s][j][k], G_tg[s][j][k], G_t[j][k]: the hi and lo rows of the stacks added
-    auto Gg = [&](int s, int j, int k) { return gd[(32 * s + j) * 96 + k] + gd[(64 + 32 * s + j) * 96 + k]; };
-    auto Gtg = [&](int s, int j, int k) { return gd[(32 * s + j) * 96 + 32 + k] + gd[(64 + 32 * s + j) * 96 + 32 + k]; };
-    auto Gt = [&](int j, int k) { return gd[j * 96 + 64 + k] + gd[(32 + j) * 96 + 64 + k]; };
-    // derivative path of the first layer: kappa_bar_s[k] = sum_j W1[j][k] (G_g[s][j][k] - 4 kappa_s[k] G_tg[s][j][k])
-    const float* w1g = a.params + (int64_t)hdr_i[2] * a.P + H * xd + H;      // W1[j][k], L2-resident since the prologue
-    for (int i = tid; i < NS * H; i += B2_NT) {
-        const int s = i >> 5, k = i & 31;
-        const float kap = sm[CF::SM_W0D + s * H + k];
-        float v = 0.0f;
-        for (int j = 0; j < H; ++j) {
-            float gsum = Gg(s, j, k);
-            if (s < NA2) gsum = fmaf(-4.0f * kap, Gtg(s, j, k), gsum);
-            v = fmaf(w1g[j * H + k], gsum, v);
-        }
-        red[L::RED_KB + i] = v;
-    }
-    __syncthreads();
-
-    float* gp = a.gpart + (int64_t)hdr_i[3] * a.P;
-    // first layer, value path: (unit k, quantity t) sits in lane (k % 8) * 4 + t of chunk (k % UPT) / 8 of the four point warps
-    // of unit group k / UPT
-    auto l0 = [&](int k, int t) {
-        const int gg_ = k / UPT, ch = (k % UPT) >> 3, ln = (k & 7) * 4 + t;
-        float v = 0.0f;
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) v += red[L::RED_L0 + ((gg_ * 4 + qq) * NCH + ch) * 32 + ln];
-        return v;
-    };
-    for (int i = tid; i < H * xd; i += B2_NT) {
-        const int j = i / xd, d = i - j * xd;
-        float v = l0(j, 1 + d);
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-            if (a.axis[s] == d) v = fmaf(hdr_f[3 + d], red[L::RED_KB + s * H + j], v);
-        gp[i] = v;
-    }
-    for (int i = tid; i < H; i += B2_NT) gp[H * xd + i] = l0(i, 0);
-    int off = H * xd + H;
-    for (int i = tid; i < HH; i += B2_NT) {
-        const int j = i >> 5, k = i & 31;
-        float v = Gt(j, k);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const float kap = sm[CF::SM_W0D + s * H + k];
-            v = fmaf(kap, Gg(s, j, k), v);
-            if (s < NA2) v = fmaf(-2.0f * kap * kap, Gtg(s, j, k), v);
-        }
-        gp[off + i] = v;
-    }
-    off += HH;
-    for (int i = tid; i < 2 * H; i += B2_NT) {      // hidden bias and output weights: sums over the 128 point threads of the unit's group
-        const int j = i & 31;
-        const float* src = red + (i < H ? L::RED_B1 : L::RED_WL) + (j % UPT) * B2_NPT + (j / UPT) * 128;
-        float v = 0.0f;
-#pragma unroll 8
-        for (int p = 0; p < 128; ++p) v += src[p];
-        gp[off + i] = v;
-    }
-    off += 2 * H;
-    if (tid == 0) {
-        float v = 0.0f;
-        for (int w = 0; w < 4; ++w) v += red[L::RED_BL + w];    // warps 0-3 are unit half 0 (the only ones that count it)
-        gp[off] = v;
-    }
+    b2_finish<CF, NG>(sm, a.params + (int64_t)hdr_i[2] * a.P + H * xd + H, a.gpart + (int64_t)hdr_i[3] * a.P, xd,
+                      make_int3(a.axis[0], a.axis[1], a.axis[2]), make_float3(hdr_f[3], hdr_f[4], hdr_f[5]));
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, TMEM_COLS);

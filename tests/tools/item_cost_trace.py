@@ -50,6 +50,13 @@ def analyse(buf, name):
     out = {"tiles_mode": int(np.bincount(nt).argmax()), "prologue": float(pro.mean()), "tile_loop": float(loop[full].mean()),
            "per_tile": float((loop[full] / nt[full]).mean()), "drain": float(drain.mean()), "reduction_and_exit": float(red.mean()),
            "gap_to_next_cta": float(np.median(gaps)), "gap_mean": float(gaps.mean()), "ctas_per_sm": float(len(b) / len(np.unique(sm)))}
+    pt = loop[full] / nt[full]
+    out["per_tile_p5_p50_p95"] = [float(np.percentile(pt, q)) for q in (5, 50, 95)]
+    sm_mean = np.array([pt[sm[full] == s_].mean() for s_ in np.unique(sm[full])])
+    out["per_tile_by_sm_min_max"] = [float(sm_mean.min()), float(sm_mean.max())]
+    order_t = np.argsort(b[full, 7])
+    nq = len(order_t) // 4
+    out["per_tile_by_launch_quartile"] = [float(pt[order_t[i * nq:(i + 1) * nq]].mean()) for i in range(4)]
     tot = out["prologue"] + out["tile_loop"] + out["drain"] + out["reduction_and_exit"] + out["gap_to_next_cta"]
     out["fixed_share"] = float(1.0 - out["tile_loop"] / tot)
     res[name] = out
