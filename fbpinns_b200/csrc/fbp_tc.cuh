@@ -653,10 +653,8 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t bar_a, bar_m;
     __shared__ uint32_t tmem_slot;
-#ifdef FBP_F2_HDR
-    __shared__ int hdr_i[2];
-    __shared__ float hdr_f[9];
-#endif
+    __shared__ int hdr_i[2];                  // first pair, pair count
+    __shared__ float hdr_f[9];                // mu[3], 1/sd[3], window flag, output shift and scale
     float* exch = sm + L::OFF_EXCH;
     float* outN = sm + L::OFF_OUT;
 
@@ -666,7 +664,6 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
     const int jb = 8 * g;                   // this thread's 8 hidden units
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
-#ifdef FBP_F2_HDR
     const int xd = a.xd;
     {   // prologue: nothing computed here stays in registers (see tc_backward_kernel2)
         const ItemRec it = tc_item(a);
@@ -703,36 +700,6 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) { mu[d] = hdr_f[d]; isd[d] = hdr_f[3 + d]; }
     const float flag = hdr_f[6], un_mu = hdr_f[7], un_sd = hdr_f[8];
-#else
-    const ItemRec it = tc_item(a);
-    const int first = it.first, count = it.count, im = it.im;
-    if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);          // its latency hides under the parameter loads
-    if (tid == 32) {
-        mbar_init(&bar_a, F2_NPT);          // every epilogue thread: A(t+1) written and D(t) held in registers
-        mbar_init(&bar_m, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const int xd = a.xd;
-    const float* ss = a.sub_static + (int64_t)im * (2 * xd + 3);
-    float mu[3], isd[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        if (d < xd) {
-            const float lo = ss[d], hi = ss[xd + d];
-            mu[d] = (hi + lo) * 0.5f;
-            isd[d] = 1.0f / ((hi - lo) * 0.5f);
-        } else { mu[d] = 0.0f; isd[d] = 0.0f; }
-    }
-    const float flag = ss[2 * xd], un_mu = ss[2 * xd + 1], un_sd = ss[2 * xd + 2];
-    const float* prow = a.params + (int64_t)im * a.P;
-    tc_stage_small<CF>(sm, prow, xd, isd, a.axis, tid, F2_NT);
-    tc_stage_b<CF, false>(sm + L::OFF_B1, nullptr, prow, xd, isd, a.axis, tid, F2_NT);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tbase = tmem_slot;
-#endif
     const int ntiles = (count + TP - 1) / TP;
     if (warp < 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     else asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
