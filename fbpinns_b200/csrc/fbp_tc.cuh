@@ -850,7 +850,8 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
 #pragma unroll
                 for (int c = 0; c < C; ++c) ex[((g - 1) * C + c) * TP + r] = up[c];
             }
-            asm volatile("bar.sync 2, 512;" ::: "memory");           // the 16 epilogue warps: partial dots exchanged
+            // partial dots exchanged: only the four warps that share this quarter's 32 points meet (one named barrier per quarter)
+            asm volatile("bar.sync %0, 128;" ::"r"(2 + (warp & 3)) : "memory");
             if (g == 0) {
                 float u[C];
 #pragma unroll
@@ -876,10 +877,14 @@ __global__ void __launch_bounds__(F2_NT, 1) tc_forward_kernel2(FastArgs a) {
                     const int c = 1 + 2 * NA2 + s;
                     o[a.ext[c]] = u[c] * w + u[0] * w1[NA2 + s];
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // warpgroup 0 only: the staged tile is complete
-                float* dst = a.pair_out + (int64_t)(first + t0) * C;
-                for (int i = r; i < cnt * C; i += 128) dst[i] = outN[i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");      // ... and copied before the next tile overwrites it
+                // each warp of unit group 0 copies the 32 rows it staged (contiguous in pair_out): warp-level ordering is enough
+                __syncwarp();
+                const int lane = tid & 31, row0 = r - lane;
+                const int nrow = min(32, cnt - row0);
+                float* dst = a.pair_out + (int64_t)(first + t0 + row0) * C;
+                const float* src = outN + row0 * C;
+                for (int i = lane; i < nrow * C; i += 32) dst[i] = src[i];
+                __syncwarp();
             }
 #pragma unroll
             for (int d = 0; d < 3; ++d) z_cur[d] = z_next[d];
