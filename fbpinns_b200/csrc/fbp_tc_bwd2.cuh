@@ -320,42 +320,47 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         auto stamp = [&](int, int) {};
         auto stamp_ring = [&](int, int) {};
 #endif
+        // S0 of tile t + 1 runs at the end of tile t, BEFORE the late ring store of the quarters 2, 3: those warps otherwise idle
+        // until the weight-gradient MMAs of the quarters 0, 1 have freed the slot, and S0 + L of the next tile is what the tensor
+        // core waits for after that store (profiles/r2g_bwd_phase_trace.md)
+        float z[3], rb[C];
+        auto do_s0 = [&](int tn) {
+                // ---- S0: coordinates, window jets, cotangent of the output-layer jets ----------------------
+#pragma unroll
+                for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
+                {
+                    float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
+                    fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
+                    const bool valid = r < min(TP, count - tn * TP);
+                    float G[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) G[c] = valid ? pf_g[c] : 0.0f;
+                    float ub0 = G[0] * w;
+#pragma unroll
+                    for (int s = 0; s < NA2; ++s) {
+                        const float G1 = G[1 + 2 * s], G2 = G[2 + 2 * s];
+                        ub0 += G1 * w1[s] + G2 * w2[s];
+                        rb[1 + 2 * s] = un_sd * (G1 * w + 2.0f * G2 * w1[s]);
+                        rb[2 + 2 * s] = un_sd * (G2 * w);
+                    }
+#pragma unroll
+                    for (int s = 0; s < NA1; ++s) {
+                        const int c = 1 + 2 * NA2 + s;
+                        ub0 += G[c] * w1[NA2 + s];
+                        rb[c] = un_sd * (G[c] * w);
+                    }
+                    rb[0] = un_sd * ub0;
+                    if (g == 0) blacc += rb[0];
+                }
+            load_idx((tn + 1) * TP);
+        };
+        if (ntiles > 0) do_s0(0);
         for (int t = 0; t < ntiles; ++t) {
             const int t0 = t * TP;
             const int cnt = min(TP, count - t0);
             const uint32_t par = (uint32_t)(t & 1);
             stamp(t, 0);
 
-            // ---- S0: coordinates, window jets, cotangent of the output-layer jets ----------------------
-            float z[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) z[d] = d < xd ? (pf_x[d] - mu[d]) * isd[d] : 0.0f;
-            float rb[C];
-            {
-                float w, w1[NS > 0 ? NS : 1], w2[NA2 > 0 ? NA2 : 1];
-                fast_window<CF>(z, isd, xd, flag, a.axis, w, w1, w2);
-                const bool valid = r < cnt;
-                float G[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) G[c] = valid ? pf_g[c] : 0.0f;
-                float ub0 = G[0] * w;
-#pragma unroll
-                for (int s = 0; s < NA2; ++s) {
-                    const float G1 = G[1 + 2 * s], G2 = G[2 + 2 * s];
-                    ub0 += G1 * w1[s] + G2 * w2[s];
-                    rb[1 + 2 * s] = un_sd * (G1 * w + 2.0f * G2 * w1[s]);
-                    rb[2 + 2 * s] = un_sd * (G2 * w);
-                }
-#pragma unroll
-                for (int s = 0; s < NA1; ++s) {
-                    const int c = 1 + 2 * NA2 + s;
-                    ub0 += G[c] * w1[NA2 + s];
-                    rb[c] = un_sd * (G[c] * w);
-                }
-                rb[0] = un_sd * ub0;
-                if (g == 0) blacc += rb[0];
-            }
-            load_idx(t0 + TP);
 
             // ---- L: t, g of this thread's 16 units; A operands of MMA 1 (t, g kappa_s, t g) -> tensor memory ----
             float tt[UPT], gg[UPT];
@@ -542,6 +547,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
                 l0acc[ch] += (dbg & 32) ? qv[0] + qv[9] + qv[18] + qv[27] : warp_transpose_reduce32(qv, lane);
             }
             stamp(t, 6);
+            if (t + 1 < ntiles) do_s0(t + 1);
             if (q >= 2 && !(dbg & 1)) ring_store();
             stamp(t, 7);
         }
