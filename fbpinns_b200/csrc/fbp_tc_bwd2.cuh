@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(B2Dim<NG>::NT, 1) tc_backward_kernel2(FastArgs
         // of every tile into the buffer passed as activation cache: [tile][8] = start, a1 arrive, m1 done, a3 arrive, ring
         // done, m3 done, E2 done, end; [512 + tile * 4 ...] = inside the ring store
 #ifdef FBP_B2_TRACE
-        const bool rec = (dbg & 64) && a.cache != nullptr && blockIdx.x == 0 && tid == 0;
+        const bool rec = (dbg & 64) && a.cache != nullptr && blockIdx.x == 0 && tid == ((dbg >> 8) & 1023);   // FBP_TC_DEBUG = 64 + 256 * thread
         const long long rec0 = clock64();
         auto stamp = [&](int t, int k) { if (rec) a.cache[t * 8 + k] = (float)(clock64() - rec0); };
         auto stamp_ring = [&](int t, int k) { if (rec) a.cache[512 + t * 4 + k] = (float)(clock64() - rec0); };

@@ -29,7 +29,8 @@ ev.forward(tr.params)
 ev.backward(ubar, tr.params, g, accumulate=False)
 torch.cuda.synchronize()
 dbgbuf = torch.zeros(64 * 8 + 64 * 4, device="cuda")
-os.environ["FBP_TC_DEBUG"] = "64"
+TID = int(sys.argv[1]) if len(sys.argv) > 1 else 0          # the recording thread: 0 = quarter 0, 64 = quarter 2 (unit group 0)
+os.environ["FBP_TC_DEBUG"] = str(64 + 256 * TID)
 tv = ev.takes.view()
 for _ in range(3):
     check(lib.fbp_backward(ev.plan.handle, C.byref(tv), ptr(ev.x), ptr(tr.params), ptr(tr.dd.sub_static), ptr(ev.grow), ptr(g), 0,
@@ -40,8 +41,8 @@ t = raw[:512].reshape(64, 8)
 rs = raw[512:].reshape(64, 4)
 nt = int((t[:, 7] > 0).sum())
 t = t[:nt]
-names = ["S0+L (-> a1 arrive)", "wait MMA1 (+gather)", "E1 (-> a3 arrive)", "ring store (q<2)", "wait MMA3", "E2", "ring store (q>=2)"]
-print(f"tiles of block 0's item: {nt}; cycles per tile (mean over tiles 1..): {np.diff(t[:, 0])[0:].mean():.0f}")
+names = ["L (-> a1 arrive)", "wait MMA1 (+gather)", "E1 (-> a3 arrive)", "ring store (q<2)", "wait MMA3", "E2", "S0 of the next tile + ring store (q>=2)"]
+print(f"thread {TID}: tiles of block 0's item: {nt}; cycles per tile (mean over tiles 1..): {np.diff(t[:, 0])[0:].mean():.0f}")
 for k, nm in enumerate(names):
     d = t[1:, k + 1] - t[1:, k]
     print(f"  {nm:24s} {d.mean():8.0f}  (min {d.min():.0f}, max {d.max():.0f})")
@@ -50,3 +51,5 @@ print("  tile boundary (end -> next start):", (t[1:, 0] - t[:-1, 7]).mean())
 rs = rs[1:nt]
 print("ring store of warp 0 (cycles): slot wait -> %0.f, TMEM reload %.0f, splits + 128 STS %.0f, proxy fence + arrive %.0f" % (
     (rs[:, 0] - t[1:nt, 3]).mean(), (rs[:, 1] - rs[:, 0]).mean(), (rs[:, 2] - rs[:, 1]).mean(), (rs[:, 3] - rs[:, 2]).mean()))
+if TID & 64:     # quarters 2, 3: the store follows E2 and S0 of the next tile
+    print("late store: E2 done -> slot acquired (S0 of the next tile + slot wait) %.0f" % (rs[:, 0] - t[1:nt, 6]).mean())
