@@ -195,6 +195,7 @@ int fbp_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_
     if (plan->use_fast())
         return fbp_fast_backward(plan, tv, d_x, d_params, d_sub_static, d_grow, d_grads, accumulate, d_gpart, d_act_cache,
                                  (cudaStream_t)stream);
+    accumulate &= ~FBP_BWD_DIRECT;        // the generic kernels have no partial buffer: they always write d_grads themselves
     FBP_REQUIRE((accumulate & ~FBP_BWD_ACCUMULATE) == 0,
                 "fbp_backward(generic): FBP_BWD_NO_REDUCE / FBP_BWD_REDUCE_ONLY need a tiled plan");
     if (plan->dev.act != FBP_ACT_TANH)

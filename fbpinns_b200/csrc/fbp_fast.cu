@@ -99,9 +99,15 @@ int fbp_fast_backward(const fbp_plan* plan, const fbp_takes_view* tv, const floa
                       const float* d_sub_static, const float* d_grow, float* d_grads, int accumulate, float* d_gpart,
                       const float* d_cache, cudaStream_t stream) {
     if (tv->m_active == 0) return 0;
+    // FBP_BWD_DIRECT: one work item per active subdomain (the caller's assertion, checked as far as the host can see):
+    // item i IS subdomain position i, the kernels write the rows of d_grads themselves and no reduction pass runs
+    const bool direct = accumulate == FBP_BWD_DIRECT;
+    FBP_REQUIRE(!(accumulate & FBP_BWD_DIRECT) || direct, "fbp_backward: FBP_BWD_DIRECT cannot be combined with other flags");
+    FBP_REQUIRE(!direct || tv->n_items_active == tv->m_active, "fbp_backward: FBP_BWD_DIRECT needs one work item per active subdomain");
+    if (direct) d_gpart = d_grads;
     FBP_REQUIRE(d_gpart != nullptr || tv->n_items_active == 0, "fbp_backward(tiled): null workspace");
     const bool run_kernels = !(accumulate & FBP_BWD_REDUCE_ONLY);
-    const bool run_reduce = !(accumulate & FBP_BWD_NO_REDUCE);
+    const bool run_reduce = !(accumulate & FBP_BWD_NO_REDUCE) && !direct;
     accumulate &= FBP_BWD_ACCUMULATE;
     if (run_kernels && tv->n_items_active > 0) {
         FastArgs a;

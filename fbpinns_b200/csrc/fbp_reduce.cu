@@ -56,9 +56,26 @@ row_sums_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_ou
     for (int v = 0; v < V; ++v) nsum[r * V + v] = N[v];
 }
 
+// Component-count specialisation of the two quotient-rule kernels: with the run-time C of the plan the per-thread jets
+// (N, D, u, acc) are indexed dynamically and live in LOCAL memory (480-byte stack frame, 32 registers: the forward kernel
+// ran at 107 us for ~300 MB at cfg 5).  CT > 0 fixes C = CT and ud = 1 at compile time: every loop unrolls, the component
+// maps i1 / i2 (run-time values of the plan) are applied with select chains, everything stays in registers.  CT = 0 is
+// the general kernel (any C, ud).  Same operations in the same order: the results are bit-identical.
+template <int CT, int N>
+__device__ __forceinline__ float jet_pick(const float (&a)[N], int i) {
+    if constexpr (CT > 0) {
+        float r = a[0];
+#pragma unroll
+        for (int k = 1; k < N; ++k) r = (i == k) ? a[k] : r;
+        return r;
+    } else {
+        return a[i];
+    }
+}
+
 // ---- forward: ujets[p] = (1/npou) sum_rows quotient_jets( sum_pairs N , D ) -------------------------
 // FROM_ROWS = false: N is summed here from the pair jets; true: N is read from precomputed row sums.
-template <bool FROM_ROWS>
+template <bool FROM_ROWS, int CT = 0>
 __global__ void __launch_bounds__(RT)
 reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ pair_out,
                       const float* __restrict__ dsum, const float* __restrict__ aff, float* __restrict__ ujets,
@@ -68,100 +85,152 @@ reduce_forward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ p
     // sharded evaluation: only the points this rank owns are reduced, into a compact array (out_row[p] = its row, < 0: skip)
     const int64_t po_ = out_row ? (int64_t)out_row[p] : p;
     if (po_ < 0) return;
-    const int C = pd.C, ud = pd.ud, V = C * ud;
-    float acc[FBP_MAX_COMP * FBP_MAX_UD];
-    for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+    constexpr int NC = CT > 0 ? CT : FBP_MAX_COMP, NV = CT > 0 ? CT : FBP_MAX_COMP * FBP_MAX_UD;
+    const int C = CT > 0 ? CT : pd.C, ud = CT > 0 ? 1 : pd.ud, V = C * ud;
+    float acc[NV];
+#pragma unroll
+    for (int v = 0; v < (CT > 0 ? CT : V); ++v) acc[v] = 0.0f;
     for (int r = tv.d_pt_row_off[p]; r < tv.d_pt_row_off[p + 1]; ++r) {
-        float N[FBP_MAX_COMP * FBP_MAX_UD];
+        float N[NV];
         if (FROM_ROWS) {
-            for (int v = 0; v < V; ++v) N[v] = pair_out[(int64_t)r * V + v];
+#pragma unroll
+            for (int v = 0; v < (CT > 0 ? CT : V); ++v) N[v] = pair_out[(int64_t)r * V + v];
         } else {
-            for (int v = 0; v < V; ++v) N[v] = 0.0f;
+#pragma unroll
+            for (int v = 0; v < (CT > 0 ? CT : V); ++v) N[v] = 0.0f;
             for (int j = tv.d_row_off[r]; j < tv.d_row_off[r + 1]; ++j) {
                 const float* po = pair_out + (int64_t)tv.d_pos[j] * V;
-                for (int v = 0; v < V; ++v) N[v] += po[v];
+#pragma unroll
+                for (int v = 0; v < (CT > 0 ? CT : V); ++v) N[v] += po[v];
             }
         }
-        float D[FBP_MAX_COMP];
-        for (int c = 0; c < C; ++c) D[c] = dsum[(int64_t)r * C + c];
+        float D[NC];
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : C); ++c) D[c] = dsum[(int64_t)r * C + c];
         const float invD = 1.0f / D[0];
         for (int o = 0; o < ud; ++o) {
-            float u[FBP_MAX_COMP];
+            float u[NC];
             u[0] = N[o] * invD;
-            for (int c = 1; c < C; ++c)
+#pragma unroll
+            for (int c = 1; c < (CT > 0 ? CT : C); ++c)
                 if (pd.ord[c] == 1) u[c] = (N[c * ud + o] - u[0] * D[c]) * invD;
-            for (int c = 1; c < C; ++c)
+#pragma unroll
+            for (int c = 1; c < (CT > 0 ? CT : C); ++c)
                 if (pd.ord[c] == 2)
-                    u[c] = (N[c * ud + o] - u[pd.i1[c]] * D[pd.i2[c]] - u[pd.i2[c]] * D[pd.i1[c]] - u[0] * D[c]) * invD;
-            for (int c = 0; c < C; ++c) acc[c * ud + o] += u[c];
+                    u[c] = (N[c * ud + o] - jet_pick<CT>(u, pd.i1[c]) * jet_pick<CT>(D, pd.i2[c])
+                            - jet_pick<CT>(u, pd.i2[c]) * jet_pick<CT>(D, pd.i1[c]) - u[0] * D[c]) * invD;
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : C); ++c) acc[c * ud + o] += u[c];
         }
     }
     const float npou = (float)tv.npou;
-    for (int v = 0; v < V; ++v) acc[v] = acc[v] / npou;
+#pragma unroll
+    for (int v = 0; v < (CT > 0 ? CT : V); ++v) acc[v] = acc[v] / npou;
     if (aff != nullptr) {
         // constraining operator A(x) u + B(x): Leibniz rule on the jets (ud == 1, checked by the launcher)
-        const float* A = aff + p * (2 * C);
-        const float* B = A + C;
-        float o[FBP_MAX_COMP];
-        for (int c = 0; c < C; ++c) {
+        float A[NC], B[NC], o[NC];
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : C); ++c) {
+            A[c] = aff[p * (2 * C) + c];
+            B[c] = aff[p * (2 * C) + C + c];
+        }
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : C); ++c) {
             float v = A[c] * acc[0] + B[c];
             if (pd.ord[c] == 1) v += A[0] * acc[c];
-            else if (pd.ord[c] == 2) v += A[pd.i1[c]] * acc[pd.i2[c]] + A[pd.i2[c]] * acc[pd.i1[c]] + A[0] * acc[c];
+            else if (pd.ord[c] == 2)
+                v += jet_pick<CT>(A, pd.i1[c]) * jet_pick<CT>(acc, pd.i2[c]) + jet_pick<CT>(A, pd.i2[c]) * jet_pick<CT>(acc, pd.i1[c])
+                     + A[0] * acc[c];
             o[c] = v;
         }
-        for (int c = 0; c < C; ++c) acc[c] = o[c];
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : C); ++c) acc[c] = o[c];
     }
-    for (int v = 0; v < V; ++v) ujets[po_ * V + v] = acc[v];
+#pragma unroll
+    for (int v = 0; v < (CT > 0 ? CT : V); ++v) ujets[po_ * V + v] = acc[v];
+}
+
+// a[i] op= x for a run-time i, without dynamic indexing when the array is to stay in registers
+template <int CT, int N>
+__device__ __forceinline__ void jet_fnma(float (&a)[N], int i, float t, float d) {      // a[i] -= t * d
+    if constexpr (CT > 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[k] = (i == k) ? a[k] - t * d : a[k];
+    } else {
+        a[i] -= t * d;
+    }
+}
+template <int CT, int N>
+__device__ __forceinline__ void jet_fma(float (&a)[N], int i, float t, float d) {       // a[i] += t * d
+    if constexpr (CT > 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[k] = (i == k) ? a[k] + t * d : a[k];
+    } else {
+        a[i] += t * d;
+    }
 }
 
 // ---- transpose: grow[r] = A(D_r)^T ujets_bar[point(r)] / npou ---------------------------------------
+template <int CT = 0>
 __global__ void __launch_bounds__(RT)
 reduce_backward_kernel(PlanDev pd, fbp_takes_view tv, const float* __restrict__ ubar_in,
                        const float* __restrict__ dsum, const float* __restrict__ aff, float* __restrict__ grow) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= tv.q) return;
-    const int C = pd.C, ud = pd.ud, V = C * ud;
+    constexpr int NC = CT > 0 ? CT : FBP_MAX_COMP;
+    const int C = CT > 0 ? CT : pd.C, ud = CT > 0 ? 1 : pd.ud, V = C * ud;
     const int pt = tv.d_np_take[r];
-    float D[FBP_MAX_COMP];
-    for (int c = 0; c < C; ++c) D[c] = dsum[r * C + c];
+    float D[NC];
+#pragma unroll
+    for (int c = 0; c < (CT > 0 ? CT : C); ++c) D[c] = dsum[r * C + c];
     const float invD = 1.0f / D[0];
     const float npou = (float)tv.npou;
     for (int o = 0; o < ud; ++o) {
-        float ub[FBP_MAX_COMP], nb[FBP_MAX_COMP];
+        float ub[NC], nb[NC];
         if (aff != nullptr) {
             // transpose of the Leibniz rule of the constraining operator (ud == 1)
-            const float* A = aff + (int64_t)pt * (2 * C);
-            float cb[FBP_MAX_COMP];
-            for (int c = 0; c < C; ++c) { cb[c] = ubar_in[(int64_t)pt * V + c]; ub[c] = 0.0f; }
-            for (int c = 0; c < C; ++c) {
+            float A[NC], cb[NC];
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : C); ++c) {
+                A[c] = aff[(int64_t)pt * (2 * C) + c];
+                cb[c] = ubar_in[(int64_t)pt * V + c];
+                ub[c] = 0.0f;
+            }
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : C); ++c) {
                 ub[0] += cb[c] * A[c];
                 if (pd.ord[c] == 1) ub[c] += cb[c] * A[0];
                 else if (pd.ord[c] == 2) {
                     ub[c] += cb[c] * A[0];
-                    ub[pd.i1[c]] += cb[c] * A[pd.i2[c]];
-                    ub[pd.i2[c]] += cb[c] * A[pd.i1[c]];
+                    jet_fma<CT>(ub, pd.i1[c], cb[c], jet_pick<CT>(A, pd.i2[c]));
+                    jet_fma<CT>(ub, pd.i2[c], cb[c], jet_pick<CT>(A, pd.i1[c]));
                 }
             }
-            for (int c = 0; c < C; ++c) ub[c] = ub[c] / npou;
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : C); ++c) ub[c] = ub[c] / npou;
         } else {
-            for (int c = 0; c < C; ++c) ub[c] = ubar_in[(int64_t)pt * V + c * ud + o] / npou;
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : C); ++c) ub[c] = ubar_in[(int64_t)pt * V + c * ud + o] / npou;
         }
-        for (int c = 1; c < C; ++c)
+#pragma unroll
+        for (int c = 1; c < (CT > 0 ? CT : C); ++c)
             if (pd.ord[c] == 2) {
                 float t = ub[c] * invD;
                 nb[c] = t;
-                ub[pd.i1[c]] -= t * D[pd.i2[c]];
-                ub[pd.i2[c]] -= t * D[pd.i1[c]];
+                jet_fnma<CT>(ub, pd.i1[c], t, jet_pick<CT>(D, pd.i2[c]));
+                jet_fnma<CT>(ub, pd.i2[c], t, jet_pick<CT>(D, pd.i1[c]));
                 ub[0] -= t * D[c];
             }
-        for (int c = 1; c < C; ++c)
+#pragma unroll
+        for (int c = 1; c < (CT > 0 ? CT : C); ++c)
             if (pd.ord[c] == 1) {
                 float t = ub[c] * invD;
                 nb[c] = t;
                 ub[0] -= t * D[c];
             }
         nb[0] = ub[0] * invD;
-        for (int c = 0; c < C; ++c) grow[r * V + c * ud + o] = nb[c];
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : C); ++c) grow[r * V + c * ud + o] = nb[c];
     }
 }
 
@@ -257,6 +326,25 @@ __global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, 
 }
 
 inline int blocks_for(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+// the component-count instance of the forward quotient-rule kernel for this plan (general kernel for ud > 1 or C > 7)
+template <bool FROM_ROWS>
+void launch_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const float* d_in, const float* d_dsum,
+                           const float* d_affine, float* d_ujets, const int32_t* d_out_row, cudaStream_t st) {
+    const int grid = blocks_for(tv->n, RT);
+#define FBP_RF(CT_) reduce_forward_kernel<FROM_ROWS, CT_><<<grid, RT, 0, st>>>(plan->dev, *tv, d_in, d_dsum, d_affine, d_ujets, d_out_row)
+    switch (plan->dev.ud == 1 ? plan->dev.C : 0) {
+        case 1: FBP_RF(1); break;
+        case 2: FBP_RF(2); break;
+        case 3: FBP_RF(3); break;
+        case 4: FBP_RF(4); break;
+        case 5: FBP_RF(5); break;
+        case 6: FBP_RF(6); break;
+        case 7: FBP_RF(7); break;
+        default: FBP_RF(0); break;
+    }
+#undef FBP_RF
+}
 #endif  // FBP_HOST_EMU
 
 }  // namespace
@@ -278,7 +366,7 @@ int fbp_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv, const flo
     FBP_REQUIRE(plan && tv, "fbp_reduce_forward: null plan/takes");
     FBP_REQUIRE(d_affine == nullptr || plan->dev.ud == 1, "fbp_reduce_forward: affine constraining needs ud == 1");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<false><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_pair_out, d_dsum, d_affine, d_ujets, nullptr);
+    launch_reduce_forward<false>(plan, tv, d_pair_out, d_dsum, d_affine, d_ujets, nullptr, (cudaStream_t)stream);
     FBP_LAUNCH_CHECK();
     return 0;
 }
@@ -296,7 +384,7 @@ int fbp_reduce_rows_forward(const fbp_plan* plan, const fbp_takes_view* tv, cons
     FBP_REQUIRE(plan && tv, "fbp_reduce_rows_forward: null plan/takes");
     FBP_REQUIRE(d_affine == nullptr || plan->dev.ud == 1, "fbp_reduce_rows_forward: affine constraining needs ud == 1");
     if (tv->n == 0) return 0;
-    reduce_forward_kernel<true><<<blocks_for(tv->n, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_nsum, d_dsum, d_affine, d_ujets, d_out_row);
+    launch_reduce_forward<true>(plan, tv, d_nsum, d_dsum, d_affine, d_ujets, d_out_row, (cudaStream_t)stream);
     FBP_LAUNCH_CHECK();
     return 0;
 }
@@ -307,7 +395,22 @@ int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const fl
     FBP_REQUIRE(d_affine == nullptr || (plan->dev.ud == 1 && tv->npou == 1),
                 "fbp_reduce_backward: affine constraining needs ud == 1 and a single partition of unity");
     if (tv->q == 0) return 0;
-    reduce_backward_kernel<<<blocks_for(tv->q, RT), RT, 0, (cudaStream_t)stream>>>(plan->dev, *tv, d_ujets_bar, d_dsum, d_affine, d_grow);
+    {
+        const int grid = blocks_for(tv->q, RT);
+        cudaStream_t st = (cudaStream_t)stream;
+#define FBP_RB(CT_) reduce_backward_kernel<CT_><<<grid, RT, 0, st>>>(plan->dev, *tv, d_ujets_bar, d_dsum, d_affine, d_grow)
+        switch (plan->dev.ud == 1 ? plan->dev.C : 0) {
+            case 1: FBP_RB(1); break;
+            case 2: FBP_RB(2); break;
+            case 3: FBP_RB(3); break;
+            case 4: FBP_RB(4); break;
+            case 5: FBP_RB(5); break;
+            case 6: FBP_RB(6); break;
+            case 7: FBP_RB(7); break;
+            default: FBP_RB(0); break;
+        }
+#undef FBP_RB
+    }
     FBP_LAUNCH_CHECK();
     return 0;
 }

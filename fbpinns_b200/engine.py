@@ -313,6 +313,10 @@ class DeviceTakes:
         self.item_order_fwd = torch.as_tensor(order_fwd, dtype=I32, device=dev)
         self.item_order_bwd = torch.as_tensor(order_bwd, dtype=I32, device=dev)
         self.n_items, self.n_items_active = int(items.shape[0]), nia
+        # exactly one work item per active subdomain (the large-problem case): the reverse kernels can then write the gradient
+        # rows themselves (FBP_BWD_DIRECT)
+        self.one_item_per_sub = bool(nia == self.m_active and
+                                     np.array_equal(sub_item_off[:self.m_active + 1], np.arange(self.m_active + 1)))
         # launch records of the tensor kernels: what block b needs, in one 16-byte load (first pair, pair count, global
         # subdomain index, item) instead of order -> items -> sub_ids (include/fbpinn_b200.h d_launch_*)
         ims = np.asarray(self.sub_ids_host, dtype=np.int32)
@@ -401,15 +405,27 @@ class ConstraintEvaluator:
                                      ptr(ujets), stream_ptr()), "fbp_reduce_forward")
         return ujets
 
+    # set by the step object when this evaluator is the ONLY contribution to the gradient buffer and the work list has one
+    # item per active subdomain: the reverse kernel writes the rows of `grads` itself (no zero fill, no reduction pass)
+    direct_grads = False
+
+    def supports_direct_grads(self):
+        return bool(self.takes.one_item_per_sub and self.plan.reverse_family != "generic")
+
     def backward(self, ujets_bar, params, grads, accumulate=True):
         """Cotangent of ujets -> adds (or writes) the gradients of the active subdomains into grads (m_active, P)."""
         lib = _lib.load()
+        flags = 1 if accumulate else 0
+        if self.direct_grads:
+            if not self.supports_direct_grads():
+                raise FbpError("direct_grads set on an evaluator whose work list has not one item per active subdomain")
+            flags = 8                                   # FBP_BWD_DIRECT
         tv = self.takes.view()
         ub = ujets_bar.contiguous().float()
         check(lib.fbp_reduce_backward(self.plan.handle, C.byref(tv), ptr(ub), ptr(self.dsum), ptr(self.affine),
                                       ptr(self.grow), stream_ptr()), "fbp_reduce_backward")
         check(lib.fbp_backward(self.plan.handle, C.byref(tv), ptr(self.x), ptr(params), ptr(self.decomp.sub_static),
-                               ptr(self.grow), ptr(grads), 1 if accumulate else 0, ptr(self.gpart), ptr(self.scratch),
+                               ptr(self.grow), ptr(grads), flags, ptr(self.gpart), ptr(self.scratch),
                                self.scratch_floats, ptr(self.cache), stream_ptr()), "fbp_backward")
 
     def pair_values_reference_order(self):

@@ -140,6 +140,14 @@ class UpdateStep:
                     aff = AffineConstraining.build(base.plan.jet, base.x, problem.constraining_fn, all_params)
             base.set_affine(aff)            # fused into the reduce kernels (forward Leibniz rule and its transpose)
             self.affine.append(aff)
+        # a single (unsharded) constraint whose work list has one item per active subdomain: the reverse kernel writes the rows
+        # of `grads` itself — no zero fill, no partial buffer, no reduction pass (FBP_BWD_DIRECT; FBP_DIRECT_GRADS=0 turns it off)
+        evs = inputs.evaluators
+        self.direct_grads = bool(len(evs) == 1 and not hasattr(evs[0], "ev") and hasattr(evs[0], "supports_direct_grads")
+                                 and evs[0].supports_direct_grads() and os.environ.get("FBP_DIRECT_GRADS", "1") != "0")
+        for e_ in evs:
+            if hasattr(e_, "supports_direct_grads"):
+                e_.direct_grads = self.direct_grads
 
     def _refresh_problem_views(self):
         """Problem trainables live in one flat storage buffer (updated in place by Adam).  Every step aliases it with a
@@ -177,7 +185,8 @@ class UpdateStep:
         return self.problem.loss_fn(self.all_params, cons)
 
     def _eager(self):
-        self.grads.zero_()
+        if not self.direct_grads:
+            self.grads.zero_()
         self.hook.grad = None
         loss = self.forward_loss()
         loss.backward()

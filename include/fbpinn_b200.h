@@ -53,6 +53,7 @@ extern "C" {
 #define FBP_BWD_ACCUMULATE 1
 #define FBP_BWD_NO_REDUCE 2
 #define FBP_BWD_REDUCE_ONLY 4
+#define FBP_BWD_DIRECT 8
 
 #define FBP_ACT_TANH 0            /* FCN, fbpinns/networks.py:61-68 */
 /* The reference's other Network plug-ins (generic kernel family only).  Packed parameter row: per layer W, b, then
@@ -220,7 +221,10 @@ int fbp_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const fl
 /* Reverse pass through the pairs of the ACTIVE subdomains: d_grads [m_active][P] (overwritten when
  * accumulate == 0, added to otherwise — several constraints share one gradient buffer).
  * `accumulate` is a bit set: 1 = add into d_grads; FBP_BWD_NO_REDUCE (2) = run the pair kernels of the view's work
- * list only (per-item partials stay in d_gpart); FBP_BWD_REDUCE_ONLY (4) = only sum the partials into d_grads.
+ * list only (per-item partials stay in d_gpart); FBP_BWD_REDUCE_ONLY (4) = only sum the partials into d_grads;
+ * FBP_BWD_DIRECT (8, alone) = the caller asserts that the work list has exactly ONE item per active subdomain
+ * (d_sub_item_off[i] == i): the tiled / tensor kernels then write the rows of d_grads themselves (no partial buffer, no
+ * reduction pass: 58 MB of traffic less at cfg 5); ignored by the generic family.
  * The split lets a multi-GPU host run interior and boundary work items as separate launches around the halo
  * exchange (tiled plans only).
  * d_gpart: workspace of fbp_backward_workspace_floats() floats (split-subdomain partial sums). */

@@ -26,7 +26,7 @@ extern "C" int emu_reduce_forward(const fbp_plan* plan, const fbp_takes_view* tv
 }
 extern "C" int emu_reduce_backward(const fbp_plan* plan, const fbp_takes_view* tv, const float* ubar, const float* dsum,
                                    const float* aff, float* grow) {
-    for_threads(tv->q, [&] { reduce_backward_kernel(plan->dev, *tv, ubar, dsum, aff, grow); });
+    for_threads(tv->q, [&] { reduce_backward_kernel<0>(plan->dev, *tv, ubar, dsum, aff, grow); });
     return 0;
 }
 extern "C" int emu_adam(float* params, float* mu, float* nu, const float* grads, const int32_t* row_ids, int64_t n_rows,
