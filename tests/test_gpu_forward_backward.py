@@ -400,3 +400,40 @@ def test_step_gradients_are_bit_reproducible():
             outs.append((u, g))
         for u, g in outs[1:]:
             assert torch.equal(u, outs[0][0]) and torch.equal(g, outs[0][1]), kernel
+
+
+def test_direct_gradient_write_matches_partial_buffer_path():
+    """FBP_BWD_DIRECT (one work item per active subdomain: the reverse kernels write the gradient rows themselves, no partial
+    buffer, no reduction pass) gives bit-identical gradients, for the tensor and the tiled family; the flag is refused when the
+    work list has split subdomains."""
+    import gpu_common
+    from fbpinns_b200._lib import FbpError
+    k = common.make_case(configs.cfg5_poisson(n_sub=(32, 32), n_pts=(256, 256)), seed=4)
+    for kernel in ["auto", "tiled"]:
+        dd, inp, params = gpu_common.device_case(k, kernel=kernel)
+        ev = inp.evaluators[0]
+        assert ev.takes.one_item_per_sub and ev.supports_direct_grads()
+        torch.manual_seed(3)
+        ubar = torch.randn(ev.takes.n, ev.V, device=params.device)
+        ev.forward(params)
+        g_ref = torch.full((len(inp.active_ims), params.shape[1]), float("nan"), device=params.device)
+        ev.backward(ubar, params, g_ref, accumulate=False)
+        g_dir = torch.full_like(g_ref, float("nan"))
+        ev.direct_grads = True
+        try:
+            ev.backward(ubar, params, g_dir, accumulate=True)       # the flag overrides: rows are written, not added
+        finally:
+            ev.direct_grads = False
+        torch.cuda.synchronize()
+        assert torch.equal(g_dir, g_ref), kernel
+    # a small problem: subdomains are split into several work items, the evaluator refuses the flag
+    k2 = common.make_case(configs.cfg5_poisson(n_sub=(4, 4), n_pts=(128, 128)), seed=4)
+    dd, inp, params = gpu_common.device_case(k2, kernel="auto")
+    ev = inp.evaluators[0]
+    assert not ev.takes.one_item_per_sub
+    ev.forward(params)
+    ev.direct_grads = True
+    with pytest.raises(FbpError):
+        ev.backward(torch.zeros(ev.takes.n, ev.V, device=params.device), params,
+                    torch.zeros((len(inp.active_ims), params.shape[1]), device=params.device))
+    ev.direct_grads = False
