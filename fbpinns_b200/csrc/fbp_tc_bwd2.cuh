@@ -2,9 +2,9 @@
 // including the weight gradient of the hidden matrix (the FFMA2 gradient warps of fbp_tc_bwd.cuh were the critical path:
 // 5.21 ms with them, 3.34 ms without, profiles/r2a_tc_bringup.md).
 //
-//   warps 0-7  "point warps": thread (g, p) = point row p of the 128-pair tile (= TMEM lane), hidden units [16 g, 16 g + 16)
-//   warp  8    "MMA warp":    one elected lane issues every tcgen05.mma of the CTA, driven by mbarriers
-//   (warps 9-11 complete the third warpgroup: setmaxnreg moves its registers to the point warps, 56 vs 224 per thread)
+//   warps 0 .. 4 NG - 1  "point warps": thread (g, p) = point row p of the 128-pair tile (= TMEM lane), units [UPT g, UPT (g + 1)), UPT = 32 / NG
+//   warp  4 NG           "MMA warp": one elected lane issues every tcgen05.mma of the CTA, driven by mbarriers
+//   (three more warps complete its warpgroup: setmaxnreg moves their registers to the point warps: 32 vs 112 per thread at NG = 4, the default)
 //
 // The first layer is linear in the normalised point, so its jets factor per unit k:  h1_0 = t,  h1_s = g kappa_s[k],
 // h1_ss = -2 kappa_s[k]^2 (t g)   with t = tanh(a0), g = 1 - t^2, kappa_s[k] = W0[k][axis s] / sd.  That is used three times:

@@ -262,6 +262,23 @@ def build_work_items(sub_off, m_active, tile_points, target_items, split=None):
     return items, sub_item_off, n_items_active, order_fwd, order_bwd
 
 
+def launch_records(items, order, sub_ids):
+    """Launch records of the tensor kernels (include/fbpinn_b200.h d_launch_fwd / d_launch_bwd): row b = what block b of
+    the launch needs — (first pair, pair count, global subdomain index, item) of work item order[b] — so that the kernel
+    reaches its parameters with two dependent loads instead of four (launch order -> work list -> subdomain index -> row)."""
+    items = np.asarray(items, dtype=np.int32).reshape(-1, 4)
+    order = np.asarray(order, dtype=np.int32)
+    it = items[order]
+    ims = np.asarray(sub_ids, dtype=np.int32)
+    return np.stack([it[:, 1], it[:, 2], ims[it[:, 0]], order], axis=1).astype(np.int32).reshape(-1, 4)
+
+
+def one_item_per_subdomain(sub_item_off, m_active, n_items_active):
+    """True when item i IS active subdomain position i (what FBP_BWD_DIRECT asserts to the library)."""
+    return bool(n_items_active == m_active and
+                np.array_equal(np.asarray(sub_item_off)[:m_active + 1], np.arange(m_active + 1)))
+
+
 class DeviceTakes:
     """One constraint's takes on the device: the reference-order arrays (m_take, n_take, p_take, np_take — bit-exact
     with fbpinns/trainers.py:336-391 after the per-constraint split of :544-571) and the subdomain-sorted view."""
@@ -315,17 +332,9 @@ class DeviceTakes:
         self.n_items, self.n_items_active = int(items.shape[0]), nia
         # exactly one work item per active subdomain (the large-problem case): the reverse kernels can then write the gradient
         # rows themselves (FBP_BWD_DIRECT)
-        self.one_item_per_sub = bool(nia == self.m_active and
-                                     np.array_equal(sub_item_off[:self.m_active + 1], np.arange(self.m_active + 1)))
-        # launch records of the tensor kernels: what block b needs, in one 16-byte load (first pair, pair count, global
-        # subdomain index, item) instead of order -> items -> sub_ids (include/fbpinn_b200.h d_launch_*)
-        ims = np.asarray(self.sub_ids_host, dtype=np.int32)
-
-        def launch(order):
-            it = items[order]
-            return np.stack([it[:, 1], it[:, 2], ims[it[:, 0]], order.astype(np.int32)], axis=1).astype(np.int32).reshape(-1)
-        self.launch_fwd = torch.as_tensor(launch(order_fwd), dtype=I32, device=dev)
-        self.launch_bwd = torch.as_tensor(launch(order_bwd), dtype=I32, device=dev)
+        self.one_item_per_sub = one_item_per_subdomain(sub_item_off, self.m_active, nia)
+        self.launch_fwd = torch.as_tensor(launch_records(items, order_fwd, self.sub_ids_host).reshape(-1), dtype=I32, device=dev)
+        self.launch_bwd = torch.as_tensor(launch_records(items, order_bwd, self.sub_ids_host).reshape(-1), dtype=I32, device=dev)
         self.tile_points = tile_points
         self._view = None
 

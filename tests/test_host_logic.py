@@ -9,7 +9,7 @@ import torch
 
 from oracle import ref_takes, ref_model
 from fbpinns_b200 import configs, decompositions, schedulers, _lib
-from fbpinns_b200.engine import build_work_items
+from fbpinns_b200.engine import build_work_items, launch_records, one_item_per_subdomain
 from fbpinns_b200.jets import JetSpec, get_ujs
 from fbpinns_b200.trainers import active_set_algebra
 from fbpinns_b200.constants import Constants, get_subdomain_ws
@@ -172,6 +172,36 @@ def test_work_items_cover_all_pairs():
                 assert (it[:-1, 2] % tile == 0).all()
                 assert np.array_equal(it[:, 3], np.arange(len(it)))
         assert nia == sio[30]
+
+
+def test_launch_records_resolve_the_index_chain():
+    """d_launch_* rows = what the kernels would otherwise load through launch order -> work list -> subdomain index."""
+    rng = np.random.default_rng(1)
+    counts = rng.integers(0, 3000, size=40)
+    counts[[3, 17]] = 0                                         # subdomains without pairs have no work item
+    sub_off = np.concatenate([[0], np.cumsum(counts)])
+    sub_ids = rng.permutation(200)[:40].astype(np.int32)        # position -> global subdomain index
+    for target in (1, 600):
+        items, sio, nia, of, ob = build_work_items(sub_off, 25, 128, target)
+        for order in (of, ob):
+            rec = launch_records(items, order, sub_ids)
+            assert rec.dtype == np.int32 and rec.shape == (len(order), 4)
+            for b, it in enumerate(order):
+                sp, first, count, _ = items[it]
+                assert tuple(rec[b]) == (first, count, sub_ids[sp], it)
+        # one item per active subdomain only when no active subdomain is empty or split
+        assert not one_item_per_subdomain(sio, 25, nia)         # subdomains 3 and 17 are empty
+    counts = np.full(12, 300)
+    sub_off = np.concatenate([[0], np.cumsum(counts)])
+    items, sio, nia, of, ob = build_work_items(sub_off, 12, 128, 4)
+    assert one_item_per_subdomain(sio, 12, nia)
+    items, sio, nia, of, ob = build_work_items(sub_off, 12, 128, 100)    # asks for more items: subdomains are split
+    assert nia > 12 and not one_item_per_subdomain(sio, 12, nia)
+    # an empty and a split subdomain cancel in the item COUNT, not in the map
+    sub_off = np.array([0, 0, 600, 700])
+    items, sio, nia, of, ob = build_work_items(sub_off, 3, 128, 3)
+    if nia == 3:
+        assert not one_item_per_subdomain(sio, 3, nia)
 
 
 def test_constants_reject_unknown_keys():
