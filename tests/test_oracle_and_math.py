@@ -483,6 +483,22 @@ def test_generic_and_streaming_kernels_emulated_on_cpu_match_oracle(tmp_path):
         assert float(g[m_active:].abs().max()) > 0            # the fixed subdomains do have a gradient the kernels skip
         off += nel
 
+    # ---- the component-count instances of the two quotient-rule kernels (what the GPU launches for ud = 1, C <= 7) against
+    #      the general kernels: same operations in the same order -> bit-identical, with and without an affine operator
+    aff = rng.standard_normal((n, 2 * Cj)).astype(np.float32)
+    for a_ in (None, aff):
+        ap = None if a_ is None else fp(a_)
+        u_gen, u_ct = np.full((n, Cj), np.nan, np.float32), np.full((n, Cj), np.nan, np.float32)
+        red.emu_reduce_forward(plan.handle, C.byref(tv), fp(pair_out), 0, fp(dsum), ap, fp(u_gen))
+        assert red.emu_reduce_forward_ct(plan.handle, C.byref(tv), fp(pair_out), 0, fp(dsum), ap, fp(u_ct), Cj) == 0
+        assert np.array_equal(u_gen, u_ct)
+        assert red.emu_reduce_forward_ct(plan.handle, C.byref(tv), fp(nsum), 1, fp(dsum), ap, fp(u_ct), Cj) == 0
+        assert np.array_equal(u_gen, u_ct)
+        g_gen, g_ct = np.full((q, Cj), np.nan, np.float32), np.full((q, Cj), np.nan, np.float32)
+        red.emu_reduce_backward(plan.handle, C.byref(tv), fp(ubar), fp(dsum), ap, fp(g_gen))
+        assert red.emu_reduce_backward_ct(plan.handle, C.byref(tv), fp(ubar), fp(dsum), ap, fp(g_ct), Cj) == 0
+        assert np.array_equal(g_gen, g_ct)
+
     # ---- Adam on the active rows
     pr, mu, nu = params.copy(), np.zeros_like(params), np.zeros_like(params)
     rows = np.ascontiguousarray(all_ims[:m_active], dtype=np.int32)

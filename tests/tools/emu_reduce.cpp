@@ -34,3 +34,33 @@ extern "C" int emu_adam(float* params, float* mu, float* nu, const float* grads,
     for_threads(n_rows * row_len, [&] { adam_kernel(params, mu, nu, grads, row_ids, n_rows, row_len, count, lr, b1, b2, eps, eps_root); });
     return 0;
 }
+
+// The component-count instances (CT = C, ud = 1: everything in registers on the GPU) against the general kernels above.
+#define EMU_CT_SWITCH(ct, CALL)                                                                          \
+    switch (ct) {                                                                                        \
+        case 1: { constexpr int CT = 1; CALL; } break;                                                   \
+        case 2: { constexpr int CT = 2; CALL; } break;                                                   \
+        case 3: { constexpr int CT = 3; CALL; } break;                                                   \
+        case 4: { constexpr int CT = 4; CALL; } break;                                                   \
+        case 5: { constexpr int CT = 5; CALL; } break;                                                   \
+        case 6: { constexpr int CT = 6; CALL; } break;                                                   \
+        case 7: { constexpr int CT = 7; CALL; } break;                                                   \
+        default: return 1;                                                                               \
+    }
+extern "C" int emu_reduce_forward_ct(const fbp_plan* plan, const fbp_takes_view* tv, const float* pair_out_or_rows, int from_rows,
+                                     const float* dsum, const float* aff, float* ujets, int ct) {
+    if (ct != plan->dev.C || plan->dev.ud != 1) return 2;
+    if (from_rows) {
+        EMU_CT_SWITCH(ct, for_threads(tv->n, [&] { reduce_forward_kernel<true, CT>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets, nullptr); }))
+    } else {
+        EMU_CT_SWITCH(ct, for_threads(tv->n, [&] { reduce_forward_kernel<false, CT>(plan->dev, *tv, pair_out_or_rows, dsum, aff, ujets, nullptr); }))
+    }
+    return 0;
+}
+extern "C" int emu_reduce_backward_ct(const fbp_plan* plan, const fbp_takes_view* tv, const float* ubar, const float* dsum,
+                                      const float* aff, float* grow, int ct) {
+    if (ct != plan->dev.C || plan->dev.ud != 1) return 2;
+    EMU_CT_SWITCH(ct, for_threads(tv->q, [&] { reduce_backward_kernel<CT>(plan->dev, *tv, ubar, dsum, aff, grow); }))
+    return 0;
+}
+
