@@ -580,6 +580,10 @@ __device__ __forceinline__ void tc_stage_small(float* sm, const float* __restric
     if (tid == 0) sm[CF::SM_BL] = prow[off + 2 * H];
 }
 
+// element i of the staging pass (lane = i % 32) -> W1[j][k]: lane bits = (j & 3, k & 3, bit 2 of j), the rest of i = (j >> 3, k >> 2)
+__host__ __device__ constexpr int stage_b_row(int i) { return (((i >> 5) & 3) << 3) | ((((i & 31) >> 4) & 1) << 2) | (i & 3); }
+__host__ __device__ constexpr int stage_b_col(int i) { return (((i >> 5) >> 2) << 2) | (((i & 31) >> 2) & 3); }
+
 // B operands, hi / lo, canonical K-major layout:  b1[v][n = j][k] = W1[j][k] sc1_v[k]  (sc1 = 1, -2 kappa_s^2),  and, for the
 // reverse kernel,  b2[v][n = k][j] = W1[j][k] sc2_v[k]  (sc2 = 1, kappa_s, -2 kappa_s^2).  Lane -> (j, k) is chosen so that the
 // 32 stores of a warp hit 32 (b1) / 16 (b2) different banks.
@@ -589,9 +593,7 @@ __device__ __forceinline__ void tc_stage_b(float* b1, float* b2, const float* __
     constexpr int NS = CF::NS, NA2 = CF::NA2, NB1 = 1 + NA2, NB2 = 1 + NS + NA2, HH = H * H;
     const float* w1 = prow + H * xd + H;
     for (int i = tid; i < HH; i += nt) {
-        const int ln = i & 31, grp = i >> 5;
-        const int j = ((grp & 3) << 3) | (((ln >> 4) & 1) << 2) | (ln & 3);
-        const int k = ((grp >> 2) << 2) | ((ln >> 2) & 3);
+        const int j = stage_b_row(i), k = stage_b_col(i);
         const float w = w1[j * H + k];
         float kap[NS > 0 ? NS : 1];
 #pragma unroll

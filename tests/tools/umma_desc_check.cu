@@ -52,6 +52,31 @@ int main() {
             if (seen != 0xffffffffu) ++bad;
         }
     }
+    {   // staging pass of the B operands (tc_stage_b): every W1[j][k] exactly once; the 32 stores of a warp hit 32 different banks
+        // for B1[n = j][k] and at least 16 for B2[n = k][j]
+        unsigned char seen[32][32] = {};
+        for (int i = 0; i < 1024; ++i) seen[fbptc::stage_b_row(i)][fbptc::stage_b_col(i)]++;
+        for (int j = 0; j < 32; ++j)
+            for (int k = 0; k < 32; ++k)
+                if (seen[j][k] != 1) ++bad;
+        for (int w = 0; w < 32; ++w) {
+            unsigned b1 = 0, b2 = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int j = fbptc::stage_b_row(32 * w + l), k = fbptc::stage_b_col(32 * w + l);
+                b1 |= 1u << (fbptc::bcore_index(j, k) & 31);
+                b2 |= 1u << (fbptc::bcore_index(k, j) & 31);
+            }
+            if (b1 != 0xffffffffu || __builtin_popcount(b2) < 16) ++bad;
+        }
+    }
+    // operand descriptors as base + constant (desc_advance) = the descriptor of the advanced address, over the whole shared memory
+    for (uint32_t base : {0x400u, 0x5480u, 0x11480u})
+        for (uint32_t off : {0u, 288u, 4608u, 73728u, 147440u}) {
+            if (fbptc::desc_advance(fbptc::make_smem_desc(base, fbptc::GK_LBO, fbptc::GK_SBO), off) !=
+                fbptc::make_smem_desc(base + off, fbptc::GK_LBO, fbptc::GK_SBO)) ++bad;
+            if (fbptc::desc_advance(fbptc::make_smem_desc(base, fbptc::B_LBO, fbptc::B_SBO), off) !=
+                fbptc::make_smem_desc(base + off, fbptc::B_LBO, fbptc::B_SBO)) ++bad;
+        }
     printf(bad ? "MISMATCH\n" : "OK\n");
     return bad ? 1 : 0;
 }
